@@ -227,7 +227,7 @@ int64_t mapad_format_xa(const mapad_index* ix, const mapad_results* res, uint64_
 
 enum {
   MAPAD_BATCH_WANT_HITS = 1u,      /* also return every hit interval with its edit operations */
-  MAPAD_BATCH_DEVICE_INPUT = 2u,   /* seq/qual/offsets/seeds are DEVICE pointers already resident in HBM */
+  MAPAD_BATCH_RESIDENT = 2u,       /* `in` is ignored: re-run on the batch the previous call left resident in HBM */
   MAPAD_BATCH_NO_D2H = 4u          /* leave results on the device (bench: kernel-only timing) */
 };
 

@@ -1,0 +1,665 @@
+// mapad_gpu.cu — CUDA kernels (sm_100a) and the C ABI of include/mapad_gpu.h.
+//
+// Kernel inventory (SURVEY.md §2 "New sm_100a kernels"):
+//   k_penalties   K1a  penalty rows: SimpleAncientDnaModel::get on the device, optimal scores
+//   k_darray      K1b  BiDArray::new: 15 offset scans per read, one scan per lane of a 16-lane group
+//   k_search      K2   k_mismatch_search: persistent threads, one read per thread, dynamic read queue,
+//                      min-max heap + edit tree in a per-thread HBM workspace, hit extraction
+//   k_epilogue    K3   intervals_to_bam: best hit, SA locate, strand / contig, MAPQ, CIGAR / MD / NM, alts
+//   k_gather      roofline denominator: independent random sector gathers
+// There is no CPU fallback: every entry point fails with MAPAD_ENODEV without a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mapad_gpu.h"
+#include "dev_index_build.hpp"
+#include "epilogue_core.cuh"
+#include "host_index.hpp"
+#include "host_params.hpp"
+
+using namespace mapad;
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+struct ReadMid {  // what K2 hands to K3
+  uint32_t n_hits, hit_off, frames_popped, flags;
+};
+struct Cursors {  // device-side bump allocators and queues
+  uint32_t queue_head;
+  uint32_t n_deferred;
+  uint32_t hit_cursor;
+  uint32_t op_cursor;
+  uint32_t cigar_cursor;
+  uint32_t text_cursor;
+  uint32_t overflow;   // bit0: hits/ops pool, bit1: cigar/text pool
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(256) k_penalties(DevParams P, ReadBatch rb, const float* __restrict__ qual2prob,
+                                                   PenRow* __restrict__ delta, float* __restrict__ dpen) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp; r < rb.n_reads; r += n_warps) {
+    const uint64_t o = rb.offsets[r];
+    const int L = (int)(rb.offsets[r + 1] - o);
+    for (int j = lane; j < L; j += 32) penalty_row(P, qual2prob, rb, o, j, L, delta, dpen);
+  }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_darray(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ dpen,
+                                                float* __restrict__ dcomp, uint32_t* __restrict__ d_steps) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t group = gid >> 4, l16 = gid & 15;
+  const uint32_t n_groups = (gridDim.x * blockDim.x) >> 4;
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
+  for (uint64_t r = group; r < rb.n_reads; r += n_groups) {
+    const uint64_t o = rb.offsets[r];
+    const int L = (int)(rb.offsets[r + 1] - o);
+    const int split = L > 0 ? alignment_start(P, rb, r, L) : 0;
+    uint32_t steps = 0;
+    for (int half = 0; half < 2; ++half) {
+      const int part_len = half == 0 ? split : L - split;
+      float* dout = dcomp + o + (half == 0 ? 0 : split);
+      if (l16 == 0 && part_len > 0) dout[0] = 0.0f;
+      DScan sc;
+      dscan_init<WIDE>(ix, sc, (int)l16);
+      for (int idx = 0; idx + 1 < part_len; ++idx) {
+        float v = 0.0f;
+        if (l16 < 15 && (int)l16 <= idx) {
+          dscan_step<WIDE>(ix, sc, half, idx, L, rb.seq + o, dpen + o, steps);
+          v = sc.z;
+        }
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1) v = fmin_rs(v, __shfl_xor_sync(mask, v, d, 16));
+        if (l16 == 0) dout[idx + 1] = v;
+      }
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) steps += __shfl_xor_sync(mask, steps, d, 16);
+    if (l16 == 0) d_steps[r] = steps;
+  }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(128) k_search(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table,
+                                                const PenRow* __restrict__ delta, const float* __restrict__ dcomp,
+                                                HeapEnt* heap_base, NodeT<WIDE>* node_base, HitTmp* hit_base, uint32_t cap,
+                                                const uint32_t* __restrict__ work_list, uint32_t n_work, uint32_t* deferred_list,
+                                                Cursors* cur, ReadMid* mid, mapad_hit* hit_pool, uint32_t hit_cap,
+                                                mapad_edit_op* op_pool, uint32_t op_cap) {
+  const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Workspace<WIDE> ws;
+  ws.heap = heap_base + slot * cap;
+  ws.nodes = node_base + slot * cap;
+  ws.hits = hit_base + slot * MAPAD_MAX_HITS;
+  ws.cap = cap;
+  while (true) {
+    const uint32_t w = atomicAdd(&cur->queue_head, 1u);
+    if (w >= n_work) break;
+    const uint32_t r = work_list ? work_list[w] : w;
+    const uint64_t o = rb.offsets[r];
+    const int L = (int)(rb.offsets[r + 1] - o);
+    ReadMid m;
+    m.n_hits = 0; m.hit_off = 0; m.frames_popped = 0; m.flags = 0;
+    if (L > 0) {
+      const int split = alignment_start(P, rb, r, L);
+      SearchState<WIDE> st;
+      SearchCounters ctr;
+      const int rc = search_read<WIDE>(ix, P, bound_table, rb.seq + o, L, split, delta + o, dcomp + o, ws, st, ctr);
+      if (rc != 0) {  // workspace too small: hand the read to the next lane
+        deferred_list[atomicAdd(&cur->n_deferred, 1u)] = r;
+        continue;
+      }
+      m.frames_popped = ctr.frames_popped;
+      m.flags = (ctr.limit_hit ? 1u : 0u) | (work_list ? 2u : 0u);
+      m.n_hits = st.n_hits;
+      if (st.n_hits) {
+        m.hit_off = atomicAdd(&cur->hit_cursor, st.n_hits);
+        for (uint32_t h = 0; h < st.n_hits; ++h) {
+          uint32_t n_left;
+          const uint32_t total = path_length<WIDE>(ws.nodes, ws.hits[h].node, split, n_left);
+          const uint32_t op_off = atomicAdd(&cur->op_cursor, total);
+          if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(ws.nodes, ws.hits[h].node, split, total, n_left, op_pool + op_off);
+          else atomicOr(&cur->overflow, 1u);
+          if ((uint64_t)m.hit_off + h < hit_cap) {
+            mapad_hit mh;
+            mh.lower = ws.hits[h].lower; mh.lower_rev = ws.hits[h].lower_rev; mh.size = ws.hits[h].size;
+            mh.alignment_score = ws.hits[h].score; mh.edit_off = op_off; mh.edit_len = total; mh.reserved = 0;
+            hit_pool[m.hit_off + h] = mh;
+          } else {
+            atomicOr(&cur->overflow, 1u);
+          }
+        }
+      }
+    }
+    mid[r] = m;
+  }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(128) k_epilogue(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table,
+                                                  const ReadMid* __restrict__ mid, const uint32_t* __restrict__ d_steps,
+                                                  const mapad_hit* __restrict__ hit_pool, const mapad_edit_op* __restrict__ op_pool,
+                                                  OutPools pools, mapad_record* __restrict__ records) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rb.n_reads) return;
+  const ReadMid m = mid[r];
+  const int L = (int)(rb.offsets[r + 1] - rb.offsets[r]);
+  mapad_record rec;
+  rec.lf_steps = 0;
+  epilogue_read<WIDE>(ix, P, bound_table, L, rb.seeds ? rb.seeds[r] : 0u, hit_pool + m.hit_off, m.n_hits, op_pool, pools, rec);
+  rec.hit_off = m.hit_off;
+  rec.n_hits = m.n_hits;
+  rec.frames_popped = m.frames_popped;
+  rec.d_ext_steps = d_steps[r];
+  rec.flags = m.flags;
+  records[r] = rec;
+}
+
+// Roofline denominator: every thread issues independent, uniformly random, `V`*16-byte loads.
+template <int V>
+__global__ void __launch_bounds__(256) k_gather(const uint4* __restrict__ table, uint64_t n_units, uint64_t per_thread, uint64_t seed,
+                                                unsigned long long* sink) {
+  uint64_t x = seed + (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull;
+  uint32_t acc = 0;
+  for (uint64_t i = 0; i < per_thread; ++i) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;  // xorshift64
+    const uint64_t u = __umul64hi(x, n_units);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      uint4 t = __ldg(table + u * V + v);
+      acc += t.x ^ t.y ^ t.z ^ t.w;
+    }
+  }
+  if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+namespace {
+
+template <class T>
+struct DevBuf {  // grow-only device buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T>
+struct PinBuf {  // grow-only pinned host buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct mapad_gpu {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  IndexMeta meta;
+  uint8_t* d_blob = nullptr;
+  bool own_blob = false;
+  mapad_params params;
+  // resident batch
+  uint64_t n_reads = 0, total_bases = 0;
+  BatchPrep prep;
+  bool have_batch = false;
+  DevBuf<uint8_t> d_seq, d_qual;
+  DevBuf<uint64_t> d_offsets;
+  DevBuf<uint32_t> d_seeds;
+  DevBuf<int16_t> d_starts;
+  DevBuf<float> d_custom, d_bound, d_qualtab, d_dpen, d_dcomp;
+  DevBuf<PenRow> d_delta;
+  DevBuf<uint32_t> d_dsteps, d_deferred_a, d_deferred_b;
+  DevBuf<ReadMid> d_mid;
+  DevBuf<Cursors> d_cur;
+  DevBuf<uint8_t> d_ws;  // workspace pool shared by all lanes
+  DevBuf<mapad_hit> d_hits;
+  DevBuf<mapad_edit_op> d_ops;
+  DevBuf<uint32_t> d_cigar;
+  DevBuf<char> d_text;
+  DevBuf<mapad_record> d_records;
+  bool has_seeds = false;
+  // pinned staging
+  PinBuf<uint8_t> h_seq, h_qual;
+  PinBuf<uint64_t> h_offsets;
+  PinBuf<uint32_t> h_seeds;
+  PinBuf<mapad_record> h_records;
+  PinBuf<mapad_hit> h_hits;
+  PinBuf<mapad_edit_op> h_ops;
+  PinBuf<uint32_t> h_cigar;
+  PinBuf<char> h_text;
+  PinBuf<Cursors> h_cur;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t ws_budget = 0;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return e_ == cudaErrorMemoryAllocation ? MAPAD_ENOMEM : MAPAD_ECUDA;                         \
+    }                                                                                              \
+  } while (0)
+
+static int pick_device(int device, std::string& err) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { err = "no CUDA device available (this library has no CPU fallback)"; return MAPAD_ENODEV; }
+  if (device < 0 || device >= n) { err = "device index out of range"; return MAPAD_EINVAL; }
+  return MAPAD_OK;
+}
+
+static int init_handle(mapad_gpu* h, int device) {
+  h->device = device;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->n_sm = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const char* env = getenv("MAPAD_WS_BYTES");
+  size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : std::min<size_t>(free_b / 3, (size_t)48 << 30);
+  h->ws_budget = std::max<size_t>(budget, (size_t)64 << 20);
+  return MAPAD_OK;
+}
+
+extern "C" {
+
+int mapad_gpu_create(const mapad_index* index, const mapad_params* params, int device, mapad_gpu** out) {
+  if (!index || !params || !out) return MAPAD_EINVAL;
+  *out = nullptr;
+  std::string err;
+  int rc = pick_device(device, err);
+  if (rc) { fprintf(stderr, "mapad_gpu_create: %s\n", err.c_str()); return rc; }
+  mapad_gpu* h = new (std::nothrow) mapad_gpu();
+  if (!h) return MAPAD_ENOMEM;
+  rc = init_handle(h, device);
+  if (rc) { fprintf(stderr, "mapad_gpu_create: %s\n", h->err.c_str()); mapad_gpu_destroy(h); return rc; }
+  h->params = *params;
+  std::vector<uint8_t> blob;
+  const char* fw = getenv("MAPAD_FORCE_WIDE");
+  rc = build_device_blob(*reinterpret_cast<const HostIndex*>(index), h->meta, blob, fw && fw[0] == '1' ? 1 : -1);
+  if (rc) { mapad_gpu_destroy(h); return rc; }
+  cudaError_t e = cudaMalloc(&h->d_blob, blob.size());
+  if (e != cudaSuccess) { mapad_gpu_destroy(h); return MAPAD_ENOMEM; }
+  h->own_blob = true;
+  e = cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { mapad_gpu_destroy(h); return MAPAD_ECUDA; }
+  *out = h;
+  return MAPAD_OK;
+}
+
+uint64_t mapad_gpu_index_meta_size(void) { return sizeof(IndexMeta); }
+
+int mapad_gpu_export_index(mapad_gpu* h, void* meta_out, void** dev_ptr_out, uint64_t* dev_bytes_out) {
+  if (!h || !meta_out || !dev_ptr_out || !dev_bytes_out) return MAPAD_EINVAL;
+  memcpy(meta_out, &h->meta, sizeof(IndexMeta));
+  *dev_ptr_out = h->d_blob;
+  *dev_bytes_out = h->meta.total_bytes;
+  return MAPAD_OK;
+}
+
+int mapad_gpu_create_from_device_blob(const void* meta, void* dev_ptr, uint64_t dev_bytes, int take_ownership,
+                                      const mapad_index* /*contigs_and_symbols*/, const mapad_params* params, int device,
+                                      mapad_gpu** out) {
+  if (!meta || !dev_ptr || !params || !out) return MAPAD_EINVAL;
+  *out = nullptr;
+  std::string err;
+  int rc = pick_device(device, err);
+  if (rc) return rc;
+  mapad_gpu* h = new (std::nothrow) mapad_gpu();
+  if (!h) return MAPAD_ENOMEM;
+  rc = init_handle(h, device);
+  if (rc) { mapad_gpu_destroy(h); return rc; }
+  memcpy(&h->meta, meta, sizeof(IndexMeta));
+  if (h->meta.total_bytes != dev_bytes) { mapad_gpu_destroy(h); return MAPAD_EINDEX; }
+  h->params = *params;
+  h->d_blob = (uint8_t*)dev_ptr;
+  h->own_blob = take_ownership != 0;
+  *out = h;
+  return MAPAD_OK;
+}
+
+int mapad_gpu_set_params(mapad_gpu* h, const mapad_params* params) {
+  if (!h || !params) return MAPAD_EINVAL;
+  h->params = *params;
+  return MAPAD_OK;
+}
+
+int mapad_gpu_set_stream(mapad_gpu* h, void* cuda_stream) {
+  if (!h) return MAPAD_EINVAL;
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (cuda_stream) { h->stream = (cudaStream_t)cuda_stream; h->own_stream = false; }
+  else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return MAPAD_ECUDA; h->own_stream = true; }
+  return MAPAD_OK;
+}
+
+const char* mapad_gpu_last_error(const mapad_gpu* h) { return h ? h->err.c_str() : "null handle"; }
+
+void mapad_gpu_destroy(mapad_gpu* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->own_blob && h->d_blob) cudaFree(h->d_blob);
+  h->d_seq.release(); h->d_qual.release(); h->d_offsets.release(); h->d_seeds.release(); h->d_starts.release();
+  h->d_custom.release(); h->d_bound.release(); h->d_qualtab.release(); h->d_dpen.release(); h->d_dcomp.release();
+  h->d_delta.release(); h->d_dsteps.release(); h->d_deferred_a.release(); h->d_deferred_b.release(); h->d_mid.release();
+  h->d_cur.release(); h->d_ws.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
+  h->d_records.release();
+  h->h_seq.release(); h->h_qual.release(); h->h_offsets.release(); h->h_seeds.release(); h->h_records.release();
+  h->h_hits.release(); h->h_ops.release(); h->h_cigar.release(); h->h_text.release(); h->h_cur.release();
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+}  // extern "C"
+
+// ---- batch pipeline ---------------------------------------------------------------------------------
+static int upload_batch(mapad_gpu* h, const mapad_reads* in) {
+  int rc = prepare_batch(h->params, *in, h->prep);
+  if (rc) { h->err = "invalid read batch"; return rc; }
+  const uint64_t n = in->n_reads, tb = h->prep.total_bases;
+  const uint64_t base0 = n ? in->offsets[0] : 0;
+  h->n_reads = n; h->total_bases = tb;
+  CK(h->h_seq.reserve(tb + 1)); CK(h->h_qual.reserve(tb + 1)); CK(h->h_offsets.reserve(n + 1));
+  CK(h->d_seq.reserve(tb + 1)); CK(h->d_qual.reserve(tb + 1)); CK(h->d_offsets.reserve(n + 1));
+  if (tb) { memcpy(h->h_seq.p, in->seq + base0, tb); memcpy(h->h_qual.p, in->qual + base0, tb); }
+  for (uint64_t r = 0; r <= n; ++r) h->h_offsets.p[r] = n ? in->offsets[r] - base0 : 0;
+  CK(cudaMemcpyAsync(h->d_seq.p, h->h_seq.p, tb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_qual.p, h->h_qual.p, tb, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_offsets.p, h->h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  h->has_seeds = in->seeds != nullptr;
+  if (h->has_seeds) {
+    CK(h->h_seeds.reserve(n + 1)); CK(h->d_seeds.reserve(n + 1));
+    memcpy(h->h_seeds.p, in->seeds, n * 4);
+    CK(cudaMemcpyAsync(h->d_seeds.p, h->h_seeds.p, n * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (!h->prep.starts.empty()) {
+    CK(h->d_starts.reserve(n + 1));
+    CK(cudaMemcpyAsync(h->d_starts.p, h->prep.starts.data(), n * 2, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (h->prep.dp.model == MODEL_TABLE) {
+    CK(h->d_custom.reserve(4 * tb + 4));
+    const float* src = in->custom_penalties ? in->custom_penalties + 4 * base0 : h->prep.custom_pen.data();
+    CK(cudaMemcpyAsync(h->d_custom.p, src, 4 * tb * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(h->d_bound.reserve(h->prep.bound_table.size()));
+  CK(cudaMemcpyAsync(h->d_bound.p, h->prep.bound_table.data(), h->prep.bound_table.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(h->d_qualtab.reserve(256));
+  CK(cudaMemcpyAsync(h->d_qualtab.p, h->prep.qual_table, 256 * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // prep.* host vectors may be reused afterwards
+  h->have_batch = true;
+  return MAPAD_OK;
+}
+
+template <bool WIDE>
+static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
+  const uint64_t n = h->n_reads, tb = h->total_bases;
+  const DevParams& P = h->prep.dp;
+  uint64_t launches = 0;
+  DevIndex ix{h->meta, h->d_blob};
+  ReadBatch rb;
+  rb.n_reads = n; rb.seq = h->d_seq.p; rb.qual = h->d_qual.p; rb.offsets = h->d_offsets.p;
+  rb.seeds = h->has_seeds ? h->d_seeds.p : nullptr;
+  rb.starts = h->prep.starts.empty() ? nullptr : h->d_starts.p;
+  rb.custom_pen = P.model == MODEL_TABLE ? h->d_custom.p : nullptr;
+  CK(h->d_delta.reserve(tb + 1)); CK(h->d_dpen.reserve(tb + 1)); CK(h->d_dcomp.reserve(tb + 1));
+  CK(h->d_dsteps.reserve(n + 1)); CK(h->d_mid.reserve(n + 1)); CK(h->d_cur.reserve(1)); CK(h->h_cur.reserve(1));
+  CK(h->d_deferred_a.reserve(n + 1)); CK(h->d_deferred_b.reserve(n + 1));
+  CK(h->d_records.reserve(n + 1));
+  // output pools (grown and the batch re-run if a cursor overshoots)
+  size_t hit_cap = std::max(h->d_hits.cap, (size_t)(4 * n + 1024));
+  size_t op_cap = std::max(h->d_ops.cap, (size_t)(4 * tb + 64 * n + 1024));
+  size_t cig_cap = std::max(h->d_cigar.cap, (size_t)(8 * n + 1024));
+  size_t text_cap = std::max(h->d_text.cap, (size_t)(24 * n + 1024));
+  CK(cudaEventRecord(h->ev[1], h->stream));
+  if (n) {
+    // ---- K1: prologue ----
+    {
+      const int block = 256;
+      const uint64_t warps_needed = n;
+      int grid = (int)std::min<uint64_t>((warps_needed * 32 + block - 1) / block, (uint64_t)h->n_sm * 32);
+      k_penalties<<<grid, block, 0, h->stream>>>(P, rb, h->d_qualtab.p, h->d_delta.p, h->d_dpen.p);
+      ++launches;
+      grid = (int)std::min<uint64_t>((n * 16 + block - 1) / block, (uint64_t)h->n_sm * 32);
+      k_darray<WIDE><<<grid, block, 0, h->stream>>>(ix, P, rb, h->d_dpen.p, h->d_dcomp.p, h->d_dsteps.p);
+      ++launches;
+    }
+  }
+  CK(cudaEventRecord(h->ev[2], h->stream));
+  for (int attempt = 0;; ++attempt) {
+    CK(h->d_hits.reserve(hit_cap)); CK(h->d_ops.reserve(op_cap)); CK(h->d_cigar.reserve(cig_cap)); CK(h->d_text.reserve(text_cap));
+    CK(cudaMemsetAsync(h->d_cur.p, 0, sizeof(Cursors), h->stream));
+    // ---- K2: search, lane by lane ----
+    const size_t per_entry = sizeof(HeapEnt) + sizeof(NodeT<WIDE>);
+    const uint64_t full_cap = (uint64_t)std::max(P.stack_limit, P.edit_tree_limit) + 32;
+    uint32_t n_work = (uint32_t)n;
+    const uint32_t* work = nullptr;
+    uint32_t* deferred = h->d_deferred_a.p;
+    uint64_t cap = 2048;
+    const char* cap_env = getenv("MAPAD_LANE0_CAP");
+    if (cap_env) cap = std::max<uint64_t>(2, strtoull(cap_env, nullptr, 10));
+    for (int lane = 0; n_work > 0; ++lane) {
+      if (cap > full_cap) cap = full_cap;
+      const int block = 128;
+      uint64_t slots_mem = h->ws_budget / (cap * per_entry + MAPAD_MAX_HITS * sizeof(HitTmp));
+      uint64_t slots = std::min<uint64_t>(slots_mem, (uint64_t)h->n_sm * 1024);
+      slots = std::min<uint64_t>(slots, ((uint64_t)n_work + block - 1) / block * block);
+      slots = slots / block * block;
+      if (slots < (uint64_t)block) {
+        if (slots_mem < 1) { h->err = "search workspace does not fit the device memory budget"; return MAPAD_ELIMIT; }
+        slots = std::min<uint64_t>(slots_mem, 32);
+      }
+      const int blk = slots >= (uint64_t)block ? block : (int)slots;
+      const int grid = (int)(slots / blk);
+      const size_t heap_bytes = (size_t)grid * blk * cap * sizeof(HeapEnt);
+      const size_t node_bytes = (size_t)grid * blk * cap * sizeof(NodeT<WIDE>);
+      const size_t hit_bytes = (size_t)grid * blk * MAPAD_MAX_HITS * sizeof(HitTmp);
+      CK(h->d_ws.reserve(heap_bytes + node_bytes + hit_bytes + 256));
+      HeapEnt* heap_base = reinterpret_cast<HeapEnt*>(h->d_ws.p);
+      NodeT<WIDE>* node_base = reinterpret_cast<NodeT<WIDE>*>(h->d_ws.p + ((heap_bytes + 63) & ~(size_t)63));
+      HitTmp* hit_base = reinterpret_cast<HitTmp*>(reinterpret_cast<uint8_t*>(node_base) + ((node_bytes + 63) & ~(size_t)63));
+      // reset the queue head / deferred counter for this lane
+      CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));
+      k_search<WIDE><<<grid, blk, 0, h->stream>>>(ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, heap_base, node_base, hit_base,
+                                                  (uint32_t)cap, work, n_work, deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p,
+                                                  (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
+                                                  (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu));
+      ++launches;
+      CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaGetLastError());
+      const uint32_t n_def = h->h_cur.p->n_deferred;
+      if (n_def == 0) break;
+      if (cap >= full_cap) { h->err = "read exceeded the full-size search workspace"; return MAPAD_ELIMIT; }
+      work = deferred;
+      deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
+      n_work = n_def;
+      cap *= 16;
+    }
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    // ---- K3: epilogue ----
+    if (n) {
+      OutPools pools;
+      pools.cigar = h->d_cigar.p; pools.cigar_cap = (uint32_t)std::min<size_t>(h->d_cigar.cap, 0xffffffffu);
+      pools.cigar_cursor = &h->d_cur.p->cigar_cursor;
+      pools.text = h->d_text.p; pools.text_cap = (uint32_t)std::min<size_t>(h->d_text.cap, 0xffffffffu);
+      pools.text_cursor = &h->d_cur.p->text_cursor;
+      pools.overflow = &h->d_cur.p->pad;
+      const int block = 128;
+      const int grid = (int)((n + block - 1) / block);
+      k_epilogue<WIDE><<<grid, block, 0, h->stream>>>(ix, P, rb, h->d_bound.p, h->d_mid.p, h->d_dsteps.p, h->d_hits.p, h->d_ops.p, pools,
+                                                      h->d_records.p);
+      ++launches;
+    }
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    const Cursors c = *h->h_cur.p;
+    const bool over = c.hit_cursor > h->d_hits.cap || c.op_cursor > h->d_ops.cap || c.cigar_cursor > h->d_cigar.cap ||
+                      c.text_cursor > h->d_text.cap || (c.overflow & 1u) || c.pad;
+    if (!over) break;
+    if (attempt >= 3) { h->err = "output pools overflowed repeatedly"; return MAPAD_ELIMIT; }
+    hit_cap = std::max<size_t>(hit_cap, (size_t)c.hit_cursor * 2 + 1024);
+    op_cap = std::max<size_t>(op_cap, (size_t)c.op_cursor * 2 + 1024);
+    cig_cap = std::max<size_t>(cig_cap, (size_t)c.cigar_cursor * 2 + 1024);
+    text_cap = std::max<size_t>(text_cap, (size_t)c.text_cursor * 2 + 1024);
+  }
+  // ---- D2H ----
+  const Cursors c = *h->h_cur.p;
+  memset(out, 0, sizeof *out);
+  out->n_reads = n;
+  if (!(flags & MAPAD_BATCH_NO_D2H)) {
+    CK(h->h_records.reserve(n + 1));
+    CK(cudaMemcpyAsync(h->h_records.p, h->d_records.p, n * sizeof(mapad_record), cudaMemcpyDeviceToHost, h->stream));
+    CK(h->h_cigar.reserve(c.cigar_cursor + 1)); CK(h->h_text.reserve(c.text_cursor + 1));
+    CK(cudaMemcpyAsync(h->h_cigar.p, h->d_cigar.p, (size_t)c.cigar_cursor * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_text.p, h->d_text.p, c.text_cursor, cudaMemcpyDeviceToHost, h->stream));
+    if (flags & MAPAD_BATCH_WANT_HITS) {
+      CK(h->h_hits.reserve(c.hit_cursor + 1)); CK(h->h_ops.reserve(c.op_cursor + 1));
+      CK(cudaMemcpyAsync(h->h_hits.p, h->d_hits.p, (size_t)c.hit_cursor * sizeof(mapad_hit), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(h->h_ops.p, h->d_ops.p, (size_t)c.op_cursor * sizeof(mapad_edit_op), cudaMemcpyDeviceToHost, h->stream));
+      out->hits = h->h_hits.p; out->n_hits = c.hit_cursor;
+      out->edit_ops = h->h_ops.p; out->n_edit_ops = c.op_cursor;
+    }
+    out->records = h->h_records.p;
+    out->cigar = h->h_cigar.p; out->n_cigar = c.cigar_cursor;
+    out->text = h->h_text.p; out->n_text = c.text_cursor;
+  }
+  CK(cudaEventRecord(h->ev[5], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&out->ms_h2d, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&out->ms_prologue, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&out->ms_search, h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&out->ms_epilogue, h->ev[3], h->ev[4]);
+  cudaEventElapsedTime(&out->ms_d2h, h->ev[4], h->ev[5]);
+  cudaEventElapsedTime(&out->ms_total, h->ev[0], h->ev[5]);
+  out->gpu_launches = launches;
+  return MAPAD_OK;
+}
+
+extern "C" {
+
+int mapad_gpu_map_batch(mapad_gpu* h, const mapad_reads* in, uint32_t flags, mapad_results* out) {
+  if (!h || !out) return MAPAD_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return MAPAD_ECUDA; }
+  CK(cudaEventRecord(h->ev[0], h->stream));
+  if (!(flags & MAPAD_BATCH_RESIDENT)) {
+    if (!in) return MAPAD_EINVAL;
+    int rc = upload_batch(h, in);
+    if (rc) return rc;
+  } else if (!h->have_batch) {
+    h->err = "MAPAD_BATCH_RESIDENT without a previously uploaded batch";
+    return MAPAD_EINVAL;
+  }
+  return h->meta.wide ? run_batch<true>(h, flags, out) : run_batch<false>(h, flags, out);
+}
+
+int mapad_gpu_gather_peak(int device, uint64_t table_bytes, uint32_t bytes_per_access, uint64_t n_accesses, double* gbps_out) {
+  if (!gbps_out || (bytes_per_access != 16 && bytes_per_access != 32 && bytes_per_access != 64)) return MAPAD_EINVAL;
+  std::string err;
+  int rc = pick_device(device, err);
+  if (rc) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return MAPAD_ECUDA;
+  uint4* table = nullptr;
+  unsigned long long* sink = nullptr;
+  table_bytes = std::max<uint64_t>(table_bytes / 64 * 64, 1 << 20);
+  if (cudaMalloc(&table, table_bytes) != cudaSuccess) return MAPAD_ENOMEM;
+  if (cudaMalloc(&sink, 8) != cudaSuccess) { cudaFree(table); return MAPAD_ENOMEM; }
+  cudaMemset(table, 1, table_bytes);
+  cudaMemset(sink, 0, 8);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  const int block = 256, grid = prop.multiProcessorCount * 8;
+  const uint64_t threads = (uint64_t)block * grid;
+  const uint64_t per_thread = std::max<uint64_t>(1, n_accesses / threads);
+  const uint64_t n_units = table_bytes / bytes_per_access;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best_ms = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    cudaEventRecord(e0);
+    if (bytes_per_access == 16) k_gather<1><<<grid, block>>>(table, n_units, per_thread, 1234 + it, sink);
+    else if (bytes_per_access == 32) k_gather<2><<<grid, block>>>(table, n_units, per_thread, 1234 + it, sink);
+    else k_gather<4><<<grid, block>>>(table, n_units, per_thread, 1234 + it, sink);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(table); cudaFree(sink); return MAPAD_ECUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(table); cudaFree(sink);
+  *gbps_out = (double)per_thread * threads * bytes_per_access / (best_ms * 1e-3) / 1e9;
+  return MAPAD_OK;
+}
+
+int64_t mapad_format_xa(const mapad_index* index, const mapad_results* res, uint64_t read_idx, char* buf, uint64_t cap) {
+  if (!index || !res || !buf || read_idx >= res->n_reads || !res->records) return MAPAD_EINVAL;
+  const HostIndex* ix = reinterpret_cast<const HostIndex*>(index);
+  const mapad_record& r = res->records[read_idx];
+  std::string s;
+  for (uint32_t a = 0; a < r.n_alts && a < 2; ++a) {  // mapping.rs:475-488
+    const mapad_alt& al = r.alts[a];
+    if (al.tid < 0 || (uint64_t)al.tid >= ix->contig_names.size()) return MAPAD_EINDEX;
+    s += ix->contig_names[al.tid];
+    s += al.strand ? ",-" : ",+";
+    s += std::to_string(al.pos + 1);
+    s += ",";
+    for (uint32_t i = 0; i < al.cigar_len; ++i) {
+      uint32_t v = res->cigar[al.cigar_off + i];
+      s += std::to_string(v >> 4);
+      s += "MID"[v & 15];
+    }
+    s += ",";
+    s.append(res->text + al.md_off, al.md_len);
+    s += "," + std::to_string(al.nm) + "," + std::to_string(al.interval_size) + ",";
+    char num[64];
+    snprintf(num, sizeof num, "%.2f", (double)al.alignment_score);  // Rust `{:.2}`
+    s += num;
+    s += ";";
+  }
+  if (s.size() + 1 > cap) return MAPAD_EINVAL;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int64_t)s.size();
+}
+
+}  // extern "C"

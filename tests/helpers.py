@@ -163,7 +163,7 @@ def simulate_reads(genome, n_reads, len_range, seed, library="single_stranded", 
                 r[dc] = ord("T")
                 r[dg] = ord("A")
         q = qv[rng.choice(4, size=L, p=qp)]
-        err = rng.random(L) < 10.0 ** (-q / 10.0)
+        err = rng.random(L) < 10.0 ** (-q.astype(np.float64) / 10.0)
         r[err] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(err.sum()))]
         seqs.append(r.tobytes())
         quals.append(q.tobytes())
