@@ -228,7 +228,8 @@ int64_t mapad_format_xa(const mapad_index* ix, const mapad_results* res, uint64_
 enum {
   MAPAD_BATCH_WANT_HITS = 1u,      /* also return every hit interval with its edit operations */
   MAPAD_BATCH_RESIDENT = 2u,       /* `in` is ignored: re-run on the batch the previous call left resident in HBM */
-  MAPAD_BATCH_NO_D2H = 4u          /* leave results on the device (bench: kernel-only timing) */
+  MAPAD_BATCH_NO_D2H = 4u,         /* leave results on the device (bench: kernel-only timing) */
+  MAPAD_BATCH_UPLOAD_ONLY = 8u     /* stage `in` in HBM and return; run it later with MAPAD_BATCH_RESIDENT */
 };
 
 typedef struct mapad_gpu mapad_gpu;
@@ -241,6 +242,9 @@ int mapad_gpu_create(const mapad_index* ix, const mapad_params* params, int devi
  * the host index.  `meta` is an opaque POD of mapad_gpu_index_meta_size() bytes. */
 uint64_t mapad_gpu_index_meta_size(void);
 int mapad_gpu_export_index(mapad_gpu* h, void* meta_out, void** dev_ptr_out, uint64_t* dev_bytes_out);
+/* Device-to-device copy of the index blob into a caller-owned device buffer (e.g. a torch tensor that
+ * torch.distributed then broadcasts). */
+int mapad_gpu_copy_index_to(mapad_gpu* h, void* dst_dev_ptr, uint64_t dst_bytes);
 int mapad_gpu_create_from_device_blob(const void* meta, void* dev_ptr, uint64_t dev_bytes, int take_ownership,
                                       const mapad_index* contigs_and_symbols, const mapad_params* params,
                                       int device, mapad_gpu** out);
@@ -257,6 +261,9 @@ int mapad_gpu_gather_peak(int device, uint64_t table_bytes, uint32_t bytes_per_a
                           double* gbps_out);
 
 int mapad_abi_version(void);
+/* sizeof of the ABI PODs, so that bindings can verify their mirrors: 0 params, 1 reads, 2 edit_op, 3 hit, 4 alt,
+ * 5 record, 6 results, 7 index_view */
+uint64_t mapad_abi_sizeof(int what);
 
 #ifdef __cplusplus
 }

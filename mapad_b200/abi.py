@@ -14,7 +14,7 @@ MODEL_SIMPLE_ADNA, MODEL_VINDIJA_PWM, MODEL_TEST, MODEL_CUSTOM = 0, 1, 2, 3
 LIB_SINGLE_STRANDED, LIB_DOUBLE_STRANDED = 0, 1
 BOUND_CONTINUOUS, BOUND_DISCRETE, BOUND_TEST = 0, 1, 2
 ED_INSERTION, ED_DELETION, ED_MATCH, ED_MISMATCH = 0, 1, 2, 3
-BATCH_WANT_HITS, BATCH_RESIDENT, BATCH_NO_D2H = 1, 2, 4
+BATCH_WANT_HITS, BATCH_RESIDENT, BATCH_NO_D2H, BATCH_UPLOAD_ONLY = 1, 2, 4, 8
 
 
 class Params(C.Structure):

@@ -38,6 +38,7 @@ def lib():
         P = C.POINTER
         sig = {
             "mapad_abi_version": (i32, []),
+            "mapad_abi_sizeof": (u64, [i32]),
             "mapad_params_from_cli": (i32, [P(abi.Params), C.c_char_p, f32, f32, f32, f32, f32, f32, f32, f32, u8, u8, i32, i32]),
             "mapad_sdm_get": (f32, [P(abi.Params), C.c_size_t, C.c_size_t, u8, u8, u8]),
             "mapad_sdm_representative_mismatch_penalty": (f32, [P(abi.Params)]),
@@ -51,6 +52,7 @@ def lib():
             "mapad_gpu_create": (i32, [vp, P(abi.Params), i32, P(vp)]),
             "mapad_gpu_index_meta_size": (u64, []),
             "mapad_gpu_export_index": (i32, [vp, vp, P(vp), P(u64)]),
+            "mapad_gpu_copy_index_to": (i32, [vp, vp, u64]),
             "mapad_gpu_create_from_device_blob": (i32, [vp, vp, u64, i32, vp, P(abi.Params), i32, P(vp)]),
             "mapad_gpu_set_params": (i32, [vp, P(abi.Params)]),
             "mapad_gpu_map_batch": (i32, [vp, P(abi.Reads), u32, P(abi.Results)]),
@@ -68,10 +70,10 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "mapad_abi_version", "mapad_params_from_cli", "mapad_sdm_get", "mapad_sdm_representative_mismatch_penalty",
+    "mapad_abi_version", "mapad_abi_sizeof", "mapad_params_from_cli", "mapad_sdm_get", "mapad_sdm_representative_mismatch_penalty",
     "mapad_bound_allowed_mismatches", "mapad_index_build", "mapad_index_build_with_draws", "mapad_index_from_view",
     "mapad_index_get_view", "mapad_index_free", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
-    "mapad_gpu_export_index", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
+    "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak",
 ]
 
@@ -228,6 +230,9 @@ class Mapper:
         nb = C.c_uint64()
         _check(lib().mapad_gpu_export_index(self.h, meta, C.byref(ptr), C.byref(nb)), self.h)
         return meta.raw, ptr.value, int(nb.value)
+
+    def copy_index_to(self, dst_dev_ptr, nbytes):
+        _check(lib().mapad_gpu_copy_index_to(self.h, dst_dev_ptr, nbytes), self.h)
 
     @classmethod
     def from_device_blob(cls, meta_bytes, dev_ptr, nbytes, index, params, device=0, take_ownership=False):

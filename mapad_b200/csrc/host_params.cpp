@@ -228,5 +228,12 @@ int mapad_params_from_cli(mapad_params* p, const char* library, float poisson_pr
 }
 
 int mapad_abi_version(void) { return MAPAD_ABI_VERSION; }
+uint64_t mapad_abi_sizeof(int what) {
+  switch (what) {
+    case 0: return sizeof(mapad_params); case 1: return sizeof(mapad_reads); case 2: return sizeof(mapad_edit_op);
+    case 3: return sizeof(mapad_hit); case 4: return sizeof(mapad_alt); case 5: return sizeof(mapad_record);
+    case 6: return sizeof(mapad_results); case 7: return sizeof(mapad_index_view); default: return 0;
+  }
+}
 
 }  // extern "C"

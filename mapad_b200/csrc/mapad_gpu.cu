@@ -335,6 +335,13 @@ int mapad_gpu_export_index(mapad_gpu* h, void* meta_out, void** dev_ptr_out, uin
   return MAPAD_OK;
 }
 
+int mapad_gpu_copy_index_to(mapad_gpu* h, void* dst_dev_ptr, uint64_t dst_bytes) {
+  if (!h || !dst_dev_ptr || dst_bytes < h->meta.total_bytes) return MAPAD_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(dst_dev_ptr, h->d_blob, h->meta.total_bytes, cudaMemcpyDeviceToDevice));
+  return MAPAD_OK;
+}
+
 int mapad_gpu_create_from_device_blob(const void* meta, void* dev_ptr, uint64_t dev_bytes, int take_ownership,
                                       const mapad_index* /*contigs_and_symbols*/, const mapad_params* params, int device,
                                       mapad_gpu** out) {
@@ -586,6 +593,11 @@ int mapad_gpu_map_batch(mapad_gpu* h, const mapad_reads* in, uint32_t flags, map
     if (!in) return MAPAD_EINVAL;
     int rc = upload_batch(h, in);
     if (rc) return rc;
+    if (flags & MAPAD_BATCH_UPLOAD_ONLY) {
+      memset(out, 0, sizeof *out);
+      out->n_reads = h->n_reads;
+      return MAPAD_OK;
+    }
   } else if (!h->have_batch) {
     h->err = "MAPAD_BATCH_RESIDENT without a previously uploaded batch";
     return MAPAD_EINVAL;

@@ -1,0 +1,173 @@
+"""`-m gpu`: the CUDA path, called through the C ABI (mapad_b200/libmapad_gpu.so), against the oracle
+and against the reference's own known-answer expectations.  Bit-exact on hit intervals, scores,
+edit operations, position, strand, CIGAR, MD, NM, MAPQ, X0/X1/XS/XT and the alternative hits."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from compare import compare_results
+from helpers import oracle_params, product_params, ora, revcomp, random_genome, simulate_reads
+from ref_cases import BENCH_PARAMS, INTEGRATION_PARAMS, SEARCH_CASES, cli_params
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def oracle_index_from_product(index, occ_k=128):
+    a = index.arrays()
+    return ora.OracleIndex.from_arrays(a["bwt"], a["sa_sample"], a["sa_rate"], a["extra_rows"], a["contigs"], a["orig_pos"], a["orig_sym"],
+                                       with_x=True, occ_k=occ_k)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from mapad_b200 import api as _api
+    _api.lib()
+    return _api
+
+
+def test_reference_known_answers(api):
+    """Every search known-answer case of src/map/mapping.rs:1401-2665 through the GPU."""
+    for case in SEARCH_CASES:
+        index = api.Index.build([("ref", case["ref"])])
+        oix = oracle_index_from_product(index)
+        pat = case["pattern"].encode()
+        q = bytes([case["qual"]] * len(pat))
+        want = ora.map_batch(oix, oracle_params(case), [pat], [q], seeds=[7], want_hits=True)
+        m = api.Mapper(index, product_params(case))
+        got = m.map_batch([pat], [q], seeds=[7], want_hits=True, with_xa=True)
+        m.close()
+        try:
+            compare_results(want, got)
+        except AssertionError as e:
+            raise AssertionError("%s: %s" % (case["name"], e))
+        e = case["expect"]
+        hits = got.hits_of(0)
+        if "scores_iter" in e:
+            assert [np.float32(h["score"]) for h in hits] == [np.float32(s) for s in e["scores_iter"]], case["name"]
+        if "n_hits" in e:
+            assert len(hits) == e["n_hits"]
+
+
+def test_bench_reads(api):
+    data = json.load(open(os.path.join(GOLDEN, "ref_test_bench.json")))
+    index = api.Index.build([("ref", data["ref_seq"])])
+    oix = oracle_index_from_product(index)
+    seqs = [r["pattern"].encode() for r in data["reads"]]
+    quals = [bytes([40] * len(s)) for s in seqs]
+    want = ora.map_batch(oix, oracle_params(BENCH_PARAMS), seqs, quals, want_hits=True)
+    m = api.Mapper(index, product_params(BENCH_PARAMS))
+    got = m.map_batch(seqs, quals, want_hits=True, with_xa=True)
+    compare_results(want, got)
+    assert [int(r["n_hits"]) for r in got.records] == [r["n_hits"] for r in data["reads"]]
+    m.close()
+
+
+def test_integration_fixture(api):
+    """tests/integration_tests.rs: 17 reads, 4 contigs, N in the reference, multi-mappers, indels."""
+    data = json.load(open(os.path.join(GOLDEN, "ref_integration.json")))
+    index = api.Index.build([(n, s) for n, s in data["contigs"]], draws="A")
+    oix = ora.OracleIndex.build([(n, s) for n, s in data["contigs"]], draws="A")
+    seqs, quals = [], []
+    for r in data["reads"]:
+        s, q = r["seq"], bytes(c - 33 for c in r["qual"].encode())
+        if r["flag"] & 16:
+            s, q = revcomp(s), q[::-1]
+        seqs.append(s.encode())
+        quals.append(q)
+    seeds = list(range(100, 100 + len(seqs)))
+    want = ora.map_batch(oix, oracle_params(INTEGRATION_PARAMS), seqs, quals, seeds=seeds, want_hits=True)
+    m = api.Mapper(index, product_params(INTEGRATION_PARAMS))
+    got = m.map_batch(seqs, quals, seeds=seeds, want_hits=True, with_xa=True)
+    m.close()
+    compare_results(want, got)
+    exp = {e["name"]: e for e in data["expectation"]}
+    for i, r in enumerate(data["reads"]):
+        e = exp[r["name"]]
+        s = got.record_summary(i)
+        if e["tid"] is None:
+            assert not s["mapped"] and s["mapq"] == 0
+        else:
+            assert (s["tid"], s["pos"] + 1, s["mapq"], s["cigar"], s["md"], s["x0"], s["x1"], s["xt"]) == \
+                   (e["tid"], e["pos"], e["mq"], e["cigar"], e["md"], e["x0"], e["x1"], e["xt"]), r["name"]
+            assert got.xa[i] == (e["xa"] or "")
+            if e["xs"] is not None:
+                assert np.float32(s["xs"]) == np.float32(e["xs"])
+
+
+@pytest.mark.parametrize("library,len_range,n_reads,gsize", [("single_stranded", (50, 50), 3000, 1_000_000),
+                                                             ("double_stranded", (30, 75), 2000, 400_000)])
+def test_simulated_reads_vs_oracle(api, library, len_range, n_reads, gsize):
+    genome = random_genome(gsize, seed=42)
+    cut = gsize // 3
+    index = api.Index.build([("chr1", genome[:cut]), ("chr2", genome[cut:])])
+    oix = oracle_index_from_product(index)
+    spec = cli_params(library)
+    seqs, quals = simulate_reads(genome, n_reads, len_range, seed=1001, library=library)
+    seqs[5] = seqs[5][:10] + b"N" + seqs[5][11:]
+    seqs[6] = b""
+    quals[6] = b""
+    seeds = (np.arange(len(seqs), dtype=np.uint64) * 2654435761 % (1 << 32)).astype(np.uint32)
+    want = ora.map_batch(oix, oracle_params(spec), seqs, quals, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=True)
+    m = api.Mapper(index, product_params(spec))
+    got = m.map_batch(seqs, quals, seeds=seeds, want_hits=True, with_xa=True)
+    compare_results(want, got)
+    mapped = sum(int(r["mapped"]) for r in got.records)
+    assert mapped > 0.6 * n_reads, mapped
+    # idempotence: a second pass over the resident batch returns identical records
+    from mapad_b200 import abi
+    res2 = abi.BatchResult(m.map_raw(None, abi.BATCH_RESIDENT | abi.BATCH_WANT_HITS))
+    compare_results(got, res2, label_a="pass1", label_b="pass2")
+    m.close()
+
+
+def _run_child(code, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=os.path.join(root, "tests"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+CHILD = r"""
+import numpy as np, os, sys
+sys.path.insert(0, os.path.dirname(os.getcwd())); sys.path.insert(0, os.getcwd())
+from compare import compare_results
+from helpers import oracle_params, product_params, ora, random_genome, simulate_reads
+from ref_cases import cli_params
+from mapad_b200 import api
+genome = random_genome(200000, seed=43)
+index = api.Index.build([("chr1", genome)])
+a = index.arrays()
+oix = ora.OracleIndex.from_arrays(a["bwt"], a["sa_sample"], a["sa_rate"], a["extra_rows"], a["contigs"], a["orig_pos"], a["orig_sym"])
+spec = cli_params("single_stranded")
+SPEC_EXTRA
+seqs, quals = simulate_reads(genome, 600, (30, 90), seed=77)
+seeds = np.arange(len(seqs), dtype=np.uint32)
+want = ora.map_batch(oix, oracle_params(spec), seqs, quals, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=True)
+m = api.Mapper(index, product_params(spec))
+got = m.map_batch(seqs, quals, seeds=seeds, want_hits=True, with_xa=True)
+compare_results(want, got)
+print("deferred", int(sum(1 for r in got.records if r["flags"] & 2)), "limit", int(sum(1 for r in got.records if r["flags"] & 1)))
+"""
+
+
+def test_wide_layout_and_retry_lanes(api):
+    """64-bit block layout forced on a small index; tiny first-lane workspace so most reads overflow into
+    the retry lanes; results must not change."""
+    out = _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_LANE0_CAP": "64"})
+    assert int(out.split("deferred")[1].split()[0]) > 100, out
+
+
+def test_search_limits_eviction(api):
+    """STACK_LIMIT / EDIT_TREE_LIMIT recovery (mapping.rs:1358-1380) with small limits: pop_min eviction and
+    slab key reuse must match the oracle."""
+    out = _run_child(CHILD.replace("SPEC_EXTRA", "spec['limits'] = (300, 700)"), {})
+    assert int(out.split("limit")[1].split()[0]) > 20, out
+    out = _run_child(CHILD.replace("SPEC_EXTRA", "spec['limits'] = (300, 700); spec['abort'] = True"), {})
+    assert int(out.split("limit")[1].split()[0]) > 20, out
