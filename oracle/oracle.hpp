@@ -978,6 +978,9 @@ inline void check_and_push(Frame f, usize pattern_len, int16_t alignment_start_p
 inline BinaryHeap<Hit> k_mismatch_search(const uint8_t* pattern, const uint8_t* quals, usize L, const Params& p,
                                          const Index& ix, Scratch& s, Counters* ctr) {
   static const uint8_t TGCA[4] = {'T', 'G', 'C', 'A'};  // b"ACGT".iter().rev()
+  // An empty read makes the reference index optimal_penalties[0] out of bounds (panic="abort");
+  // both the oracle and the CUDA path report such a read as unmapped instead.
+  if (L == 0) return BinaryHeap<Hit>();
   const int16_t alignment_start_pos = p.sdm.find_alignment_start(L);
   BiDArray bi_d;
   bi_d.build(pattern, quals, L, (usize)alignment_start_pos, p, ix, ctr);
