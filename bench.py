@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py — reads mapped / second of the B200 hot path (BASELINE.json metric), per the driver contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3]
+
+One "step" = one pass of the hot path (penalties + D array + search + epilogue) over one chunk of
+`--batch` simulated reads (the reference's default --batch_size is 250 000; src/main.rs:229).  Every
+step uses a different chunk; an L2 flush (256 MiB memset) separates steps.
+  value  reads/s with the chunk already resident in HBM (device time from CUDA events on the
+         library's stream, max over ranks), D2H of the records included
+  e2e    reads/s through the public C-ABI call with host buffers: H2D + kernels + D2H in the timed region
+Multi-GPU: one process per GPU (torchrun), index built once on rank 0 and broadcast with NCCL, reads
+sharded per rank (weak scaling), no data-path collective.
+`--impl reference` times the CPU restatement of mapAD 0.45.0 (oracle/, all host threads): the reference
+itself is Rust and cannot be built in this image (no rustc/cargo).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from mapad_b200 import abi, workloads  # noqa: E402
+
+
+def cli_spec(library):
+    from ref_cases import cli_params
+    return cli_params(library)
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(cfg, batch, n_batches, rank, need_index=True):
+    from mapad_b200 import api
+    t0 = time.time()
+    genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
+    index = None
+    if need_index:
+        index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234)
+    t_index = time.time() - t0
+    batches = [workloads.simulate_batch(genome, batch, cfg["len_range"], seed=cfg["seed"] * 1000 + rank * 100 + b, library=cfg["library"])
+               for b in range(n_batches)]
+    return genome, index, batches, t_index
+
+
+def oracle_index_for(index):
+    from oracle import oracle as ora
+    a = index.arrays()
+    return ora.OracleIndex.from_arrays(a["bwt"], a["sa_sample"], a["sa_rate"], a["extra_rows"], a["contigs"], a["orig_pos"], a["orig_sym"])
+
+
+def run_cpu(index, spec, packed, n_sample, threads):
+    """Times the oracle on the first n_sample reads of a chunk; returns (reads/s, seconds, n)."""
+    from helpers import oracle_params
+    from oracle import oracle as ora
+    oix = oracle_index_for(index)
+    seq, qual, off = packed
+    n = min(n_sample, len(off) - 1)
+    sub = (seq[: int(off[n])], qual[: int(off[n])], off[: n + 1])
+    p = oracle_params(spec)
+    t0 = time.time()
+    res = ora.map_batch(oix, p, None, None, seeds=np.arange(n, dtype=np.uint32), n_threads=threads, want_hits=False, packed=sub)
+    dt = time.time() - t0
+    return n / dt, dt, n, res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default=os.environ.get("MAPAD_BENCH_WORKLOAD", "cfg3"))
+    ap.add_argument("--batch", type=int, default=250_000)
+    ap.add_argument("--cpu-sample", type=int, default=20_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = dict(workloads.CONFIGS[args.workload])
+    spec = cli_spec(cfg["library"])
+    threads = os.cpu_count() or 1
+    workload_name = "%s: %s; chunk of %d reads per step" % (args.workload, cfg["desc"], args.batch)
+
+    # ------------------------------------------------------------------ reference arm (CPU restatement)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from mapad_b200 import api
+        n_steps = args.steps + args.warmup
+        sample = max(1000, min(args.batch, int(os.environ.get("MAPAD_REF_SAMPLE", "20000"))))
+        genome, index, batches, _ = build_workload(cfg, sample, n_steps, 0)
+        times, n_done = [], 0
+        for b in range(n_steps):
+            rps, dt, n, _ = run_cpu(index, spec, batches[b], sample, threads)
+            if b >= args.warmup:
+                times.append(dt); n_done += n
+        value = n_done / sum(times)
+        print(json.dumps({
+            "impl": "reference", "metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 intervals + f32 scores", "data": "synthetic",
+            "config": {"workload": workload_name, "sample": "%d reads per step (bounded sample of the chunk)" % sample},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port",
+                             "sample": "C++ restatement of mapAD 0.45.0 (reference binary not buildable here: no Rust toolchain), %d reads/step, %d threads" % (sample, threads)},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    import torch.distributed as dist
+    from helpers import product_params
+    from mapad_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    params = product_params(spec)
+    n_batches = args.warmup + args.steps
+    genome, index, batches, t_index = build_workload(cfg, args.batch, n_batches, rank, need_index=(rank == 0))
+    t0 = time.time()
+    if world == 1:
+        mapper = api.Mapper(index, params, device=local_rank)
+        blob_bytes = mapper.export_index()[2]
+    else:
+        # index replicated per GPU: built + re-laid-out on rank 0, one NCCL broadcast over NVLink
+        if rank == 0:
+            mapper0 = api.Mapper(index, params, device=local_rank)
+            meta, _, nbytes = mapper0.export_index()
+            hdr = [meta, nbytes]
+        else:
+            hdr = [None, None]
+        dist.broadcast_object_list(hdr, src=0)
+        meta, nbytes = hdr
+        blob = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            mapper0.copy_index_to(blob.data_ptr(), nbytes)
+            torch.cuda.synchronize()
+            mapper0.close()
+        dist.broadcast(blob, src=0)
+        torch.cuda.synchronize()
+        mapper = api.Mapper.from_device_blob(meta, blob.data_ptr(), nbytes, index, params, device=local_rank)
+        blob_bytes = nbytes
+    t_upload = time.time() - t0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    reads_structs = [api.make_reads(b[0], b[1], b[2], np.arange(len(b[2]) - 1, dtype=np.uint32)) for b in batches]
+
+    def step_resident(i):
+        R, _keep = reads_structs[i]
+        mapper.map_raw(R, abi.BATCH_UPLOAD_ONLY)
+        flush.fill_(i & 0xff)            # evict L2 between steps
+        torch.cuda.synchronize()
+        res = mapper.map_raw(None, abi.BATCH_RESIDENT)
+        return res
+
+    def step_e2e(i):
+        R, _keep = reads_structs[i]
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        res = mapper.map_raw(R, 0)
+        return res, time.perf_counter() - t
+
+    # ---- warm-up (untimed) ----
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed: resident ----
+    wall0 = time.perf_counter()
+    dev_ms, search_ms, prologue_ms, epilogue_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    stats = dict(P=0, E=0, W=0, search_bytes=0, total_bytes=0, mapped=0, deferred=0)
+    for i in range(args.warmup, n_batches):
+        res = step_resident(i)
+        dev_ms += res.ms_total
+        search_ms += res.ms_search; prologue_ms += res.ms_prologue; epilogue_ms += res.ms_epilogue
+        launches += int(res.gpu_launches)
+        recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
+        ab = workloads.algorithmic_bytes(recs, int(batches[i][2][-1]))
+        for k in ("P", "E", "W", "search_bytes", "total_bytes"):
+            stats[k] += ab[k]
+        stats["mapped"] += int(recs["mapped"].sum())
+        stats["deferred"] += int(((recs["flags"] & 2) != 0).sum())
+    barrier()
+    wall_resident = time.perf_counter() - wall0
+    # ---- timed: end to end through the C ABI with host buffers ----
+    e2e_s, e2e_launches = 0.0, 0
+    h2d = d2h = 0
+    for i in range(args.warmup, n_batches):
+        res, dt = step_e2e(i)
+        e2e_s += dt
+        e2e_launches += int(res.gpu_launches)
+        tb = int(batches[i][2][-1])
+        h2d = 2 * tb + 8 * (args.batch + 1) + 4 * args.batch
+        d2h = int(res.n_reads) * ctypes.sizeof(abi.Record) + 4 * int(res.n_cigar) + int(res.n_text)
+    barrier()
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s, search_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([stats["P"], stats["E"], stats["W"], stats["search_bytes"], stats["total_bytes"], stats["mapped"], launches, stats["deferred"]],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max, search_ms_max = [float(x) for x in t.tolist()]
+    P, E, W, search_bytes, total_bytes, mapped, launches_all, deferred = [float(x) for x in tot.tolist()]
+    total_reads = args.batch * args.steps * world
+    value = total_reads / (dev_ms_max * 1e-3)
+    e2e_value = total_reads / e2e_s_max
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # live denominator for random sector traffic: 64 B gathers over a table of the index size
+        try:
+            gather = api.gather_peak(local_rank, max(blob_bytes, 64 << 20), 64, 1 << 27)
+            gather32 = api.gather_peak(local_rank, max(blob_bytes, 64 << 20), 32, 1 << 27)
+        except Exception:
+            gather = gather32 = None
+        n_search_launch = max(1.0, float(args.steps))
+        achieved = (search_bytes / world / args.steps) / (search_ms_max / args.steps * 1e-3) / 1e9
+        out = {
+            "metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 intervals + f32 scores", "data": "synthetic",
+            "config": {"workload": workload_name, "l2": "256 MiB memset between steps; every step maps a different chunk",
+                       "params": "-p 0.03 -f 0.5 -t 0.5 -d 0.02 -s 1.0 -D 0.02 -i 0.001 -x 0.5 --gap_dist_ends 5 --max_num_gaps_open 2",
+                       "index_bytes_hbm": blob_bytes, "index_build_s": round(t_index, 2), "index_upload_s": round(t_upload, 3),
+                       "mapped_fraction": mapped / total_reads, "frames_popped_per_read": P / total_reads,
+                       "d_ext_steps_per_read": E / total_reads, "lf_steps_per_read": W / total_reads,
+                       "retry_lane_reads": deferred, "wall_s_resident_loop": round(wall_resident, 3)},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": search_bytes / world / args.steps, "kernel_ms_per_launch": search_ms_max / args.steps,
+                         "random_gather_peak_64B_gbs": gather, "random_gather_peak_32B_gbs": gather32,
+                         "frac_of_gather_peak": (achieved / gather) if gather else None,
+                         "path_algorithmic_gbs": (total_bytes / world) / (dev_ms_max * 1e-3) / 1e9,
+                         "ms_prologue_per_step": prologue_ms / args.steps, "ms_epilogue_per_step": epilogue_ms / args.steps},
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            rps, dt, n, _ = run_cpu(index, spec, batches[args.warmup], args.cpu_sample, threads)
+            out["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
+                                   "sample": "first %d reads of a timed chunk, %.1f s, C++ restatement of mapAD 0.45.0 (reference binary not buildable: no Rust toolchain)" % (n, dt)}
+        print(json.dumps(out))
+    mapper.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
