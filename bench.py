@@ -121,7 +121,7 @@ def run_cpu(index, spec, packed, n_sample, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default=os.environ.get("MAPAD_BENCH_WORKLOAD", "cfg3"))
@@ -211,55 +211,96 @@ def main():
 
     reads_structs = [api.make_reads(b[0], b[1], b[2], np.arange(len(b[2]) - 1, dtype=np.uint32)) for b in batches]
 
-    def step_resident(i):
-        R, _keep = reads_structs[i]
-        mapper.map_raw(R, abi.BATCH_UPLOAD_ONLY)
-        flush.fill_(i & 0xff)            # evict L2 between steps
-        torch.cuda.synchronize()
-        res = mapper.map_raw(None, abi.BATCH_RESIDENT)
-        return res
+    # Chunks are pipelined: `inflight` handles share the index blob, each owns a stream and a workspace, so the
+    # straggler reads of one chunk (per-read work is heavy-tailed: median ~1e3 frames, maximum >1e6) overlap with
+    # the next chunks.  The timed region spans from the first launch to the completion of the last chunk.
+    inflight = max(1, min(args.steps, int(os.environ.get("MAPAD_BENCH_INFLIGHT", "16"))))
+    mappers = [mapper] + [mapper.clone() for _ in range(inflight - 1)]
+    streams = [torch.cuda.Stream() for _ in mappers]
+    for mp, st in zip(mappers, streams):
+        mp.set_stream(st.cuda_stream)
 
-    def step_e2e(i):
-        R, _keep = reads_structs[i]
-        flush.fill_(i & 0xff)
+    def run_pipelined(chunk_ids, resident):
+        """Maps the given chunks, round-robin over the handles, one host thread per handle.
+        resident=True: chunks are uploaded first (untimed), the timed region re-runs them from HBM.
+        Returns (device seconds from first start to last end event, per-chunk results list, wall seconds)."""
+        per = [[] for _ in mappers]
+        for k, cid in enumerate(chunk_ids):
+            per[k % len(mappers)].append(cid)
+        if resident:
+            assert all(len(p) <= 1 for p in per), "resident timing needs one handle per chunk"
+            for mp, p in zip(mappers, per):
+                for cid in p:
+                    mp.map_raw(reads_structs[cid][0], abi.BATCH_UPLOAD_ONLY)
+        flush.fill_(1)
+        barrier()
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in mappers]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in mappers]
+        results = {}
+        errors = []
+
+        def work(h):
+            try:
+                torch.cuda.set_device(local_rank)
+                ev0[h].record(streams[h])
+                for cid in per[h]:
+                    if resident:
+                        res = mappers[h].map_raw(None, abi.BATCH_RESIDENT)
+                    else:
+                        res = mappers[h].map_raw(reads_structs[cid][0], 0)
+                    recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
+                    results[cid] = dict(recs=recs, ms_search=res.ms_search, ms_prologue=res.ms_prologue, ms_epilogue=res.ms_epilogue,
+                                        ms_total=res.ms_total, launches=int(res.gpu_launches), n_cigar=int(res.n_cigar), n_text=int(res.n_text))
+                ev1[h].record(streams[h])
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        w0 = time.perf_counter()
+        threads_ = [threading.Thread(target=work, args=(h,)) for h in range(len(mappers)) if per[h]]
+        for t_ in threads_:
+            t_.start()
+        for t_ in threads_:
+            t_.join()
         torch.cuda.synchronize()
-        t = time.perf_counter()
-        res = mapper.map_raw(R, 0)
-        return res, time.perf_counter() - t
+        wall = time.perf_counter() - w0
+        if errors:
+            raise errors[0]
+        used = [h for h in range(len(mappers)) if per[h]]
+        first = min(used, key=lambda h: ev0[used[0]].elapsed_time(ev0[h]))
+        dev_ms_ = max(ev0[first].elapsed_time(ev1[h]) for h in used)
+        return dev_ms_ * 1e-3, results, wall
 
     # ---- warm-up (untimed) ----
-    for i in range(args.warmup):
-        step_resident(i)
+    warm_ids = list(range(args.warmup))
+    for k0 in range(0, len(warm_ids), len(mappers)):
+        run_pipelined(warm_ids[k0:k0 + len(mappers)], resident=False)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- timed: resident ----
-    wall0 = time.perf_counter()
-    dev_ms, search_ms, prologue_ms, epilogue_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    timed_ids = list(range(args.warmup, n_batches))
+    # ---- timed: chunks resident in HBM ----
+    resident_ok = len(timed_ids) <= len(mappers)
+    dev_s, results, wall_resident = run_pipelined(timed_ids, resident=resident_ok)
+    dev_ms = dev_s * 1e3
+    search_ms = sum(r["ms_search"] for r in results.values())
+    prologue_ms = sum(r["ms_prologue"] for r in results.values())
+    epilogue_ms = sum(r["ms_epilogue"] for r in results.values())
+    launches = sum(r["launches"] for r in results.values())
     stats = dict(P=0, E=0, W=0, search_bytes=0, total_bytes=0, mapped=0, deferred=0)
-    for i in range(args.warmup, n_batches):
-        res = step_resident(i)
-        dev_ms += res.ms_total
-        search_ms += res.ms_search; prologue_ms += res.ms_prologue; epilogue_ms += res.ms_epilogue
-        launches += int(res.gpu_launches)
-        recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
-        ab = workloads.algorithmic_bytes(recs, int(batches[i][2][-1]))
+    for cid, r in results.items():
+        ab = workloads.algorithmic_bytes(r["recs"], int(batches[cid][2][-1]))
         for k in ("P", "E", "W", "search_bytes", "total_bytes"):
             stats[k] += ab[k]
-        stats["mapped"] += int(recs["mapped"].sum())
-        stats["deferred"] += int(((recs["flags"] & 2) != 0).sum())
+        stats["mapped"] += int(r["recs"]["mapped"].sum())
+        stats["deferred"] += int(((r["recs"]["flags"] & 2) != 0).sum())
     barrier()
-    wall_resident = time.perf_counter() - wall0
-    # ---- timed: end to end through the C ABI with host buffers ----
-    e2e_s, e2e_launches = 0.0, 0
-    h2d = d2h = 0
-    for i in range(args.warmup, n_batches):
-        res, dt = step_e2e(i)
-        e2e_s += dt
-        e2e_launches += int(res.gpu_launches)
-        tb = int(batches[i][2][-1])
-        h2d = 2 * tb + 8 * (args.batch + 1) + 4 * args.batch
-        d2h = int(res.n_reads) * ctypes.sizeof(abi.Record) + 4 * int(res.n_cigar) + int(res.n_text)
+    # ---- timed: end to end through the C ABI with host buffers (H2D + kernels + D2H inside the timed region) ----
+    e2e_dev_s, results_e2e, e2e_wall = run_pipelined(timed_ids, resident=False)
+    e2e_s = e2e_wall
+    tb = int(batches[timed_ids[0]][2][-1])
+    h2d = 2 * tb + 8 * (args.batch + 1) + 4 * args.batch
+    r0 = results_e2e[timed_ids[0]]
+    d2h = args.batch * ctypes.sizeof(abi.Record) + 4 * r0["n_cigar"] + r0["n_text"]
     barrier()
     clocks = sampler.stop()
 
@@ -290,7 +331,9 @@ def main():
         except Exception:
             gather = gather32 = None
         n_search_launch = max(1.0, float(args.steps))
-        achieved = (search_bytes / world / args.steps) / (search_ms_max / args.steps * 1e-3) / 1e9
+        # k_search launches of different chunks overlap on the device, so the dominant kernel's achieved rate is taken over
+        # the whole timed region (it accounts for >98 % of it): algorithmic bytes of all its launches / elapsed device time
+        achieved = (search_bytes / world) / (dev_ms_max * 1e-3) / 1e9
         out = {
             "metric": "reads mapped/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -300,13 +343,14 @@ def main():
                        "index_bytes_hbm": blob_bytes, "index_build_s": round(t_index, 2), "index_upload_s": round(t_upload, 3),
                        "mapped_fraction": mapped / total_reads, "frames_popped_per_read": P / total_reads,
                        "d_ext_steps_per_read": E / total_reads, "lf_steps_per_read": W / total_reads,
-                       "retry_lane_reads": deferred, "wall_s_resident_loop": round(wall_resident, 3)},
+                       "retry_lane_reads": deferred, "wall_s_resident_loop": round(wall_resident, 3),
+                       "chunks_in_flight": len(mappers), "inputs_resident_for_value": bool(resident_ok)},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": search_bytes / world / args.steps, "kernel_ms_per_launch": search_ms_max / args.steps,
+                         "algorithmic_bytes_per_launch": search_bytes / world / args.steps, "kernel_ms_per_launch_overlapped": search_ms_max / args.steps,
                          "random_gather_peak_64B_gbs": gather, "random_gather_peak_32B_gbs": gather32,
                          "frac_of_gather_peak": (achieved / gather) if gather else None,
                          "path_algorithmic_gbs": (total_bytes / world) / (dev_ms_max * 1e-3) / 1e9,
@@ -317,6 +361,8 @@ def main():
             out["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
                                    "sample": "first %d reads of a timed chunk, %.1f s, C++ restatement of mapAD 0.45.0 (reference binary not buildable: no Rust toolchain)" % (n, dt)}
         print(json.dumps(out))
+    for mp in mappers[1:]:
+        mp.close()
     mapper.close()
     if world > 1:
         dist.barrier()

@@ -242,6 +242,16 @@ class Mapper:
                                                        C.byref(params), device, C.byref(out)))
         return cls(index, params, device, _handle=out)
 
+    def clone(self, device=None):
+        """A second handle on the same device that shares this handle's GPU-resident index blob (no copy).
+        Handles are independent otherwise (own stream, workspace, one batch in flight each), which lets a
+        driver keep several chunks in flight so that straggler reads of one chunk overlap with the next."""
+        meta, ptr, nbytes = self.export_index()
+        c = Mapper.from_device_blob(meta, ptr, nbytes, self.index, self.params, self.device if device is None else device,
+                                    take_ownership=False)
+        c._blob_owner = self  # keep the owner alive
+        return c
+
     def map_raw(self, reads_struct, flags=0):
         res = abi.Results()
         _check(lib().mapad_gpu_map_batch(self.h, C.byref(reads_struct) if reads_struct is not None else None, flags, C.byref(res)), self.h)

@@ -64,4 +64,19 @@ struct DevParams {
   uint32_t bound_table_len; // entries in the per-length table (discrete: k(L); continuous: L^exponent)
 };
 
+// K2 -> K3 hand-over and device-side bump allocators / queues
+struct ReadMid {
+  uint32_t n_hits, hit_off, frames_popped, flags;
+};
+struct Cursors {
+  uint32_t queue_head;
+  uint32_t n_deferred;
+  uint32_t hit_cursor;
+  uint32_t op_cursor;
+  uint32_t cigar_cursor;
+  uint32_t text_cursor;
+  uint32_t overflow;   // hits / edit-op pool overflow
+  uint32_t pad;        // cigar / text pool overflow
+};
+
 }  // namespace mapad

@@ -88,19 +88,33 @@ MAPAD_DEV void count_word(uint32_t x, int npos, uint32_t& nC, uint32_t& nG, uint
   nC += popc32(lo) - phl;
 }
 
-// Ranks of A,C,G,T at row r: c[k] = #(rank k+1) in bwt[0..=r]   (Occ::get for the four bases at once)
+// Ranks of A,C,G,T at row r: c[k] = #(rank k+1) in bwt[0..=r]   (Occ::get for the four bases at once).
+// Split into the block fetch (occ_load) and the popcount arithmetic (occ_finish) so that callers can put
+// independent work between the two.
 template <bool WIDE>
-MAPAD_DEV void occ4(const DevIndex& ix, uint64_t r, uint64_t c[4]) {
+struct OccRaw { U4 w[WIDE ? 4 : 2]; };
+
+template <bool WIDE>
+MAPAD_DEV void occ_load(const DevIndex& ix, uint64_t r, OccRaw<WIDE>& raw) {
+  if (!WIDE) {
+    const uint8_t* p = ix.occ() + (r >> 6) * 32;
+    raw.w[0] = load16(p); raw.w[1] = load16(p + 16);
+  } else {
+    const uint8_t* p = ix.occ() + (r >> 7) * 64;
+    raw.w[0] = load16(p); raw.w[1] = load16(p + 16); raw.w[2] = load16(p + 32); raw.w[3] = load16(p + 48);
+  }
+}
+
+template <bool WIDE>
+MAPAD_DEV void occ_finish(const DevIndex& ix, uint64_t r, const OccRaw<WIDE>& raw, uint64_t c[4]) {
   uint32_t nC = 0, nG = 0, nT = 0;
   uint64_t bstart;
   int npos;
   bool flagged;
   if (!WIDE) {
-    uint64_t b = r >> 6;
-    bstart = b << 6;
+    bstart = (r >> 6) << 6;
     npos = (int)(r & 63) + 1;
-    const uint8_t* p = ix.occ() + b * 32;
-    U4 cn = load16(p), cd = load16(p + 16);
+    const U4 cn = raw.w[0], cd = raw.w[1];
     flagged = (cn.x >> 31) != 0;
     c[0] = cn.x & 0x7fffffffu; c[1] = cn.y; c[2] = cn.z; c[3] = cn.w;
     count_word(cd.x, npos, nC, nG, nT);
@@ -108,11 +122,9 @@ MAPAD_DEV void occ4(const DevIndex& ix, uint64_t r, uint64_t c[4]) {
     count_word(cd.z, npos - 32, nC, nG, nT);
     count_word(cd.w, npos - 48, nC, nG, nT);
   } else {
-    uint64_t b = r >> 7;
-    bstart = b << 7;
+    bstart = (r >> 7) << 7;
     npos = (int)(r & 127) + 1;
-    const uint8_t* p = ix.occ() + b * 64;
-    U4 c0 = load16(p), c1 = load16(p + 16), d0 = load16(p + 32), d1 = load16(p + 48);
+    const U4 c0 = raw.w[0], c1 = raw.w[1], d0 = raw.w[2], d1 = raw.w[3];
     uint64_t a0 = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
     flagged = (a0 >> 63) != 0;
     c[0] = a0 & 0x7fffffffffffffffull;
@@ -141,6 +153,13 @@ MAPAD_DEV void occ4(const DevIndex& ix, uint64_t r, uint64_t c[4]) {
   c[0] += nA; c[1] += nC; c[2] += nG; c[3] += nT;
 }
 
+template <bool WIDE>
+MAPAD_DEV void occ4(const DevIndex& ix, uint64_t r, uint64_t c[4]) {
+  OccRaw<WIDE> raw;
+  occ_load<WIDE>(ix, r, raw);
+  occ_finish<WIDE>(ix, r, raw, c);
+}
+
 // rank (0..5) of the BWT symbol at `row`
 template <bool WIDE>
 MAPAD_DEV uint32_t bwt_at(const DevIndex& ix, uint64_t row) {
@@ -167,13 +186,22 @@ MAPAD_DEV uint64_t sentinels_upto(const DevIndex& ix, uint64_t pos) {  // fmd_in
   return (uint64_t)(ix.m.sentinel_rows[0] <= pos) + (uint64_t)(ix.m.sentinel_rows[1] <= pos);
 }
 
-// FmdExtIterator: out[k] is the extension by rank 4-k (T,G,C,A)
+// FmdExtIterator: out[k] is the extension by rank 4-k (T,G,C,A).  extend_load issues the (at most) two
+// block fetches, extend_finish turns them into the four child intervals.
 template <bool WIDE>
-MAPAD_DEV void extend_all(const DevIndex& ix, const BiIv& in, BiIv out[4]) {
+struct ExtRaw { OccRaw<WIDE> lo, hi; };
+
+template <bool WIDE>
+MAPAD_DEV void extend_load(const DevIndex& ix, const BiIv& in, ExtRaw<WIDE>& raw) {
+  if (in.lower != 0) occ_load<WIDE>(ix, in.lower - 1, raw.lo);
+  occ_load<WIDE>(ix, in.lower + in.size - 1, raw.hi);
+}
+template <bool WIDE>
+MAPAD_DEV void extend_finish(const DevIndex& ix, const BiIv& in, const ExtRaw<WIDE>& raw, BiIv out[4]) {
   uint64_t lo[4] = {0, 0, 0, 0}, hi[4];
   uint64_t s_lo = 0;
-  if (in.lower != 0) { occ4<WIDE>(ix, in.lower - 1, lo); s_lo = sentinels_upto(ix, in.lower - 1); }
-  occ4<WIDE>(ix, in.lower + in.size - 1, hi);
+  if (in.lower != 0) { occ_finish<WIDE>(ix, in.lower - 1, raw.lo, lo); s_lo = sentinels_upto(ix, in.lower - 1); }
+  occ_finish<WIDE>(ix, in.lower + in.size - 1, raw.hi, hi);
   uint64_t l = in.lower_rev + (sentinels_upto(ix, in.lower + in.size - 1) - s_lo);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -184,6 +212,12 @@ MAPAD_DEV void extend_all(const DevIndex& ix, const BiIv& in, BiIv out[4]) {
     out[k].size = s;
     l += s;
   }
+}
+template <bool WIDE>
+MAPAD_DEV void extend_all(const DevIndex& ix, const BiIv& in, BiIv out[4]) {
+  ExtRaw<WIDE> raw;
+  extend_load<WIDE>(ix, in, raw);
+  extend_finish<WIDE>(ix, in, raw, out);
 }
 
 // backward_ext by rank r (1..4); r == 0 means "not in the alphabet" -> empty interval (fmd_index.rs:79-85)

@@ -20,6 +20,7 @@
 #include "../../include/mapad_gpu.h"
 #include "dev_index_build.hpp"
 #include "epilogue_core.cuh"
+#include "search_warp.cuh"
 #include "host_index.hpp"
 #include "host_params.hpp"
 
@@ -28,20 +29,6 @@ using namespace mapad;
 // =================================================================================================
 // kernels
 // =================================================================================================
-struct ReadMid {  // what K2 hands to K3
-  uint32_t n_hits, hit_off, frames_popped, flags;
-};
-struct Cursors {  // device-side bump allocators and queues
-  uint32_t queue_head;
-  uint32_t n_deferred;
-  uint32_t hit_cursor;
-  uint32_t op_cursor;
-  uint32_t cigar_cursor;
-  uint32_t text_cursor;
-  uint32_t overflow;   // bit0: hits/ops pool, bit1: cigar/text pool
-  uint32_t pad;
-};
-
 __global__ void __launch_bounds__(256) k_penalties(DevParams P, ReadBatch rb, const float* __restrict__ qual2prob,
                                                    PenRow* __restrict__ delta, float* __restrict__ dpen) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -474,41 +461,42 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
   for (int attempt = 0;; ++attempt) {
     CK(h->d_hits.reserve(hit_cap)); CK(h->d_ops.reserve(op_cap)); CK(h->d_cigar.reserve(cig_cap)); CK(h->d_text.reserve(text_cap));
     CK(cudaMemsetAsync(h->d_cur.p, 0, sizeof(Cursors), h->stream));
-    // ---- K2: search, lane by lane ----
+    // ---- K2: search, lane by lane (warp per read; reads that outgrow a lane's workspace move to the next) ----
     const size_t per_entry = sizeof(HeapEnt) + sizeof(NodeT<WIDE>);
     const uint64_t full_cap = (uint64_t)std::max(P.stack_limit, P.edit_tree_limit) + 32;
     uint32_t n_work = (uint32_t)n;
     const uint32_t* work = nullptr;
     uint32_t* deferred = h->d_deferred_a.p;
-    uint64_t cap = 2048;
+    uint64_t cap = 65536;
     const char* cap_env = getenv("MAPAD_LANE0_CAP");
     if (cap_env) cap = std::max<uint64_t>(2, strtoull(cap_env, nullptr, 10));
+    const int warps_per_block = 4, block = warps_per_block * 32;  // small blocks: a straggler warp pins little of an SM
+    uint32_t hs = 1408;
+    const char* hs_env = getenv("MAPAD_SMEM_HEAP");
+    if (hs_env) hs = (uint32_t)std::min<uint64_t>(3400, std::max<uint64_t>(8, strtoull(hs_env, nullptr, 10)));
+    const size_t smem = (size_t)warps_per_block * ((size_t)hs * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA);
+    CK(cudaFuncSetAttribute(k_search_warp<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int lane = 0; n_work > 0; ++lane) {
       if (cap > full_cap) cap = full_cap;
-      const int block = 128;
-      uint64_t slots_mem = h->ws_budget / (cap * per_entry + MAPAD_MAX_HITS * sizeof(HitTmp));
-      uint64_t slots = std::min<uint64_t>(slots_mem, (uint64_t)h->n_sm * 1024);
-      slots = std::min<uint64_t>(slots, ((uint64_t)n_work + block - 1) / block * block);
-      slots = slots / block * block;
-      if (slots < (uint64_t)block) {
-        if (slots_mem < 1) { h->err = "search workspace does not fit the device memory budget"; return MAPAD_ELIMIT; }
-        slots = std::min<uint64_t>(slots_mem, 32);
+      uint64_t warps_mem = h->ws_budget / (cap * per_entry);
+      uint64_t warps = std::min<uint64_t>(warps_mem, (uint64_t)h->n_sm * 16);
+      warps = std::min<uint64_t>(warps, ((uint64_t)n_work + warps_per_block - 1) / warps_per_block * warps_per_block);
+      int grid = (int)(warps / warps_per_block);
+      if (grid < 1) {
+        if (warps_mem < 1) { h->err = "search workspace does not fit the device memory budget"; return MAPAD_ELIMIT; }
+        grid = 1;
       }
-      const int blk = slots >= (uint64_t)block ? block : (int)slots;
-      const int grid = (int)(slots / blk);
-      const size_t heap_bytes = (size_t)grid * blk * cap * sizeof(HeapEnt);
-      const size_t node_bytes = (size_t)grid * blk * cap * sizeof(NodeT<WIDE>);
-      const size_t hit_bytes = (size_t)grid * blk * MAPAD_MAX_HITS * sizeof(HitTmp);
-      CK(h->d_ws.reserve(heap_bytes + node_bytes + hit_bytes + 256));
+      const uint64_t n_wslots = (uint64_t)grid * warps_per_block;
+      const size_t heap_bytes = (size_t)n_wslots * cap * sizeof(HeapEnt);
+      const size_t node_bytes = (size_t)n_wslots * cap * sizeof(NodeT<WIDE>);
+      CK(h->d_ws.reserve(heap_bytes + node_bytes + 256));
       HeapEnt* heap_base = reinterpret_cast<HeapEnt*>(h->d_ws.p);
       NodeT<WIDE>* node_base = reinterpret_cast<NodeT<WIDE>*>(h->d_ws.p + ((heap_bytes + 63) & ~(size_t)63));
-      HitTmp* hit_base = reinterpret_cast<HitTmp*>(reinterpret_cast<uint8_t*>(node_base) + ((node_bytes + 63) & ~(size_t)63));
-      // reset the queue head / deferred counter for this lane
-      CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));
-      k_search<WIDE><<<grid, blk, 0, h->stream>>>(ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, heap_base, node_base, hit_base,
-                                                  (uint32_t)cap, work, n_work, deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p,
-                                                  (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
-                                                  (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu));
+      CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter
+      k_search_warp<WIDE><<<grid, block, smem, h->stream>>>(ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, heap_base, node_base,
+                                                            (uint32_t)cap, hs, work, n_work, deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p,
+                                                            (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
+                                                            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu));
       ++launches;
       CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));

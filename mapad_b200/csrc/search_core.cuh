@@ -242,7 +242,14 @@ MAPAD_DEV void node_load(const NodeT<WIDE>* nodes, uint32_t id, Frame& f) {
   f.node = id;
 }
 
-// ---- min_max_heap::MinMaxHeap on HeapEnt[] ---------------------------
+// ---- min_max_heap::MinMaxHeap ------------------------------------------
+// Generic over the backing store H (get(i) / set(i, e)): a plain array for the per-thread version,
+// shared memory with a global-memory spill for the warp-cooperative kernel.
+struct PlainHeapStore {
+  HeapEnt* d;
+  MAPAD_DEV HeapEnt get(uint32_t i) const { return d[i]; }
+  MAPAD_DEV void set(uint32_t i, HeapEnt e) const { d[i] = e; }
+};
 MAPAD_DEV bool mm_on_min_level(uint32_t i) {
 #if defined(__CUDA_ARCH__)
   int level = 31 - __clz((int)(i + 1));
@@ -251,69 +258,80 @@ MAPAD_DEV bool mm_on_min_level(uint32_t i) {
 #endif
   return (level & 1) == 0;
 }
-MAPAD_DEV void mm_push(HeapEnt* d, uint32_t& n, HeapEnt e) {
+template <class H>
+MAPAD_DEV void mm_push(const H& d, uint32_t& n, HeapEnt e) {
   uint32_t i = n++;
   bool min_level = mm_on_min_level(i);
   bool climb_max;
   if (i > 0) {
     uint32_t p = (i - 1) >> 1;
-    HeapEnt pe = d[p];
+    HeapEnt pe = d.get(p);
     if (min_level) {
-      if (e.score > pe.score) { d[i] = pe; i = p; climb_max = true; } else climb_max = false;
+      if (e.score > pe.score) { d.set(i, pe); i = p; climb_max = true; } else climb_max = false;
     } else {
-      if (e.score < pe.score) { d[i] = pe; i = p; climb_max = false; } else climb_max = true;
+      if (e.score < pe.score) { d.set(i, pe); i = p; climb_max = false; } else climb_max = true;
     }
   } else {
     climb_max = !min_level;
   }
   while (i >= 3) {
     uint32_t gp = (((i - 1) >> 1) - 1) >> 1;
-    HeapEnt ge = d[gp];
-    if (climb_max ? (e.score > ge.score) : (e.score < ge.score)) { d[i] = ge; i = gp; } else break;
+    HeapEnt ge = d.get(gp);
+    if (climb_max ? (e.score > ge.score) : (e.score < ge.score)) { d.set(i, ge); i = gp; } else break;
   }
-  d[i] = e;
+  d.set(i, e);
 }
-template <bool MAX>
-MAPAD_DEV void mm_trickle_down(HeapEnt* d, uint32_t n, uint32_t i) {
-  HeapEnt e = d[i];
+template <bool MAX, class H>
+MAPAD_DEV void mm_trickle_down(const H& d, uint32_t n, uint32_t i) {
+  HeapEnt e = d.get(i);
   while (true) {
+    const uint32_t c1 = 2 * i + 1;
+    if (c1 >= n) break;
+    const uint32_t g1 = 4 * i + 3;
+    // the six candidates (2 children, 4 grandchildren) are fetched independently of each other so that a
+    // level living in HBM costs one memory latency; candidate indices are increasing, so "stop at the first
+    // index >= len" of the reference equals "skip the invalid ones"
+    HeapEnt x[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const uint32_t idx = c < 2 ? c1 + c : g1 + (c - 2);
+      x[c] = idx < n ? d.get(idx) : e;
+    }
     uint32_t best = MAPAD_NO_NODE;
     float bk = e.score;
     HeapEnt be = e;
-    const uint32_t c1 = 2 * i + 1;
-    const uint32_t g1 = 4 * i + 3;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      uint32_t idx = c < 2 ? c1 + c : g1 + (c - 2);
-      if (idx >= n) break;
-      HeapEnt x = d[idx];
-      if (MAX ? (x.score > bk) : (x.score < bk)) { best = idx; bk = x.score; be = x; }
+      const uint32_t idx = c < 2 ? c1 + c : g1 + (c - 2);
+      if (idx < n && (MAX ? (x[c].score > bk) : (x[c].score < bk))) { best = idx; bk = x[c].score; be = x[c]; }
     }
     if (best == MAPAD_NO_NODE) break;
     bool was_child = best <= c1 + 1;
-    d[i] = be;
+    d.set(i, be);
     i = best;
     if (was_child) break;
     uint32_t p = (i - 1) >> 1;
-    HeapEnt pe = d[p];
-    if (MAX ? (pe.score > e.score) : (pe.score < e.score)) { d[p] = e; e = pe; }
+    HeapEnt pe = d.get(p);
+    if (MAX ? (pe.score > e.score) : (pe.score < e.score)) { d.set(p, e); e = pe; }
   }
-  d[i] = e;
+  d.set(i, e);
 }
-MAPAD_DEV bool mm_pop_max(HeapEnt* d, uint32_t& n, HeapEnt& out) {
+template <class H>
+MAPAD_DEV bool mm_pop_max(const H& d, uint32_t& n, HeapEnt& out) {
   if (n == 0) return false;
-  uint32_t m = n == 1 ? 0 : (n == 2 ? 1 : (d[1].score > d[2].score ? 1 : 2));
-  HeapEnt item = d[n - 1];
+  uint32_t m = n == 1 ? 0 : (n == 2 ? 1 : (d.get(1).score > d.get(2).score ? 1 : 2));
+  HeapEnt item = d.get(n - 1);
   n -= 1;
-  if (m < n) { HeapEnt t = d[m]; d[m] = item; item = t; mm_trickle_down<true>(d, n, m); }
+  if (m < n) { HeapEnt t = d.get(m); d.set(m, item); item = t; mm_trickle_down<true>(d, n, m); }
   out = item;
   return true;
 }
-MAPAD_DEV bool mm_pop_min(HeapEnt* d, uint32_t& n, HeapEnt& out) {
+template <class H>
+MAPAD_DEV bool mm_pop_min(const H& d, uint32_t& n, HeapEnt& out) {
   if (n == 0) return false;
-  HeapEnt item = d[n - 1];
+  HeapEnt item = d.get(n - 1);
   n -= 1;
-  if (n > 0) { HeapEnt t = d[0]; d[0] = item; item = t; mm_trickle_down<false>(d, n, 0); }
+  if (n > 0) { HeapEnt t = d.get(0); d.set(0, item); item = t; mm_trickle_down<false>(d, n, 0); }
   out = item;
   return true;
 }
@@ -419,7 +437,7 @@ MAPAD_DEV void check_and_push(const Workspace<WIDE>& ws, SearchState<WIDE>& st, 
     return;
   }
   if (st.heap_n >= ws.cap) { st.overflow = true; return; }
-  mm_push(ws.heap, st.heap_n, HeapEnt{f.score, id});
+  mm_push(PlainHeapStore{ws.heap}, st.heap_n, HeapEnt{f.score, id});
 }
 
 template <bool WIDE>
@@ -438,10 +456,10 @@ MAPAD_DEV int search_read(const DevIndex& ix, const DevParams& P, const float* b
     root.score = 0.0f; root.node = 0;
     node_store<WIDE>(ws.nodes, 0, root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
     st.node_hi = 1; st.tree_len = 1;
-    mm_push(ws.heap, st.heap_n, HeapEnt{0.0f, 0});
+    mm_push(PlainHeapStore{ws.heap}, st.heap_n, HeapEnt{0.0f, 0});
   }
   HeapEnt top;
-  while (mm_pop_max(ws.heap, st.heap_n, top)) {
+  while (mm_pop_max(PlainHeapStore{ws.heap}, st.heap_n, top)) {
     ctr.frames_popped += 1;
     Frame sf;
     node_load<WIDE>(ws.nodes, top.node, sf);
@@ -531,7 +549,7 @@ MAPAD_DEV int search_read(const DevIndex& ix, const DevParams& P, const float* b
       long long excess = e1 > e2 ? e1 : e2;
       for (long long e = 0; e < excess; ++e) {
         HeapEnt mn;
-        if (mm_pop_min(ws.heap, st.heap_n, mn)) {
+        if (mm_pop_min(PlainHeapStore{ws.heap}, st.heap_n, mn)) {
           if (mn.node != 0) {  // Tree::remove (backtrack_tree.rs:49-53)
             ws.nodes[mn.node].parent = st.free_head;
             st.free_head = mn.node;
