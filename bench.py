@@ -215,6 +215,10 @@ def main():
     # straggler reads of one chunk (per-read work is heavy-tailed: median ~1e3 frames, maximum >1e6) overlap with
     # the next chunks.  The timed region spans from the first launch to the completion of the last chunk.
     inflight = max(1, min(args.steps, int(os.environ.get("MAPAD_BENCH_INFLIGHT", "16"))))
+    free_b, _total_b = torch.cuda.mem_get_info()
+    os.environ["MAPAD_WS_BYTES"] = str(int(min(free_b * 0.7 / inflight, 24 << 30)))  # search workspace budget per handle
+    mapper.close()
+    mapper = api.Mapper(index, params, device=local_rank) if world == 1 else api.Mapper.from_device_blob(meta, blob.data_ptr(), nbytes, index, params, device=local_rank)
     mappers = [mapper] + [mapper.clone() for _ in range(inflight - 1)]
     streams = [torch.cuda.Stream() for _ in mappers]
     for mp, st in zip(mappers, streams):
@@ -271,7 +275,8 @@ def main():
         return dev_ms_ * 1e-3, results, wall
 
     # ---- warm-up (untimed) ----
-    warm_ids = list(range(args.warmup))
+    # every handle maps at least one warm-up chunk so that all its buffers exist before the timed region
+    warm_ids = [i % max(1, args.warmup) for i in range(max(args.warmup, len(mappers)))]
     for k0 in range(0, len(warm_ids), len(mappers)):
         run_pipelined(warm_ids[k0:k0 + len(mappers)], resident=False)
     barrier()

@@ -20,6 +20,7 @@
 #include "../../include/mapad_gpu.h"
 #include "dev_index_build.hpp"
 #include "epilogue_core.cuh"
+#include "search_pool.cuh"
 #include "search_warp.cuh"
 #include "host_index.hpp"
 #include "host_params.hpp"
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) k_search(DevIndex ix, DevParams P, ReadBa
                                                 mapad_edit_op* op_pool, uint32_t op_cap) {
   const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   Workspace<WIDE> ws;
-  ws.heap = heap_base + slot * cap;
+  ws.heap_ = heap_base + slot * cap;
   ws.nodes = node_base + slot * cap;
   ws.hits = hit_base + slot * MAPAD_MAX_HITS;
   ws.cap = cap;
@@ -113,9 +114,9 @@ __global__ void __launch_bounds__(128) k_search(DevIndex ix, DevParams P, ReadBa
         m.hit_off = atomicAdd(&cur->hit_cursor, st.n_hits);
         for (uint32_t h = 0; h < st.n_hits; ++h) {
           uint32_t n_left;
-          const uint32_t total = path_length<WIDE>(ws.nodes, ws.hits[h].node, split, n_left);
+          const uint32_t total = path_length<WIDE>(ws, ws.hits[h].node, split, n_left);
           const uint32_t op_off = atomicAdd(&cur->op_cursor, total);
-          if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(ws.nodes, ws.hits[h].node, split, total, n_left, op_pool + op_off);
+          if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(ws, ws.hits[h].node, split, total, n_left, op_pool + op_off);
           else atomicOr(&cur->overflow, 1u);
           if ((uint64_t)m.hit_off + h < hit_cap) {
             mapad_hit mh;
@@ -179,11 +180,11 @@ template <class T>
 struct DevBuf {  // grow-only device buffer
   T* p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t n) {
+  cudaError_t reserve(size_t n, bool exact = false) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = n + n / 4 + 64;
+    size_t want = exact ? n : n + n / 4 + 64;
     cudaError_t e = cudaMalloc(&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
@@ -232,6 +233,8 @@ struct mapad_gpu {
   DevBuf<ReadMid> d_mid;
   DevBuf<Cursors> d_cur;
   DevBuf<uint8_t> d_ws;  // workspace pool shared by all lanes
+  DevBuf<uint32_t> d_pool_next, d_pool_tables;
+  DevBuf<HitTmp> d_pool_hits;
   DevBuf<mapad_hit> d_hits;
   DevBuf<mapad_edit_op> d_ops;
   DevBuf<uint32_t> d_cigar;
@@ -283,6 +286,7 @@ static int init_handle(mapad_gpu* h, int device) {
   const char* env = getenv("MAPAD_WS_BYTES");
   size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : std::min<size_t>(free_b / 3, (size_t)48 << 30);
   h->ws_budget = std::max<size_t>(budget, (size_t)64 << 20);
+  CK(h->d_ws.reserve(h->ws_budget + 4096, true));  // one allocation up front: lanes only partition it
   return MAPAD_OK;
 }
 
@@ -374,7 +378,7 @@ void mapad_gpu_destroy(mapad_gpu* h) {
   h->d_seq.release(); h->d_qual.release(); h->d_offsets.release(); h->d_seeds.release(); h->d_starts.release();
   h->d_custom.release(); h->d_bound.release(); h->d_qualtab.release(); h->d_dpen.release(); h->d_dcomp.release();
   h->d_delta.release(); h->d_dsteps.release(); h->d_deferred_a.release(); h->d_deferred_b.release(); h->d_mid.release();
-  h->d_cur.release(); h->d_ws.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
+  h->d_cur.release(); h->d_ws.release(); h->d_pool_next.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
   h->d_records.release();
   h->h_seq.release(); h->h_qual.release(); h->h_offsets.release(); h->h_seeds.release(); h->h_records.release();
   h->h_hits.release(); h->h_ops.release(); h->h_cigar.release(); h->h_text.release(); h->h_cur.release();
@@ -476,6 +480,46 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     if (hs_env) hs = (uint32_t)std::min<uint64_t>(3400, std::max<uint64_t>(8, strtoull(hs_env, nullptr, 10)));
     const size_t smem = (size_t)warps_per_block * ((size_t)hs * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA);
     CK(cudaFuncSetAttribute(k_search_warp<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ---- throughput lane: one read per THREAD, workspaces grown in 64 KiB chunks from a pool that spans the whole
+    //      workspace budget; reads that outgrow `max_nodes` restart in the warp-cooperative lanes below ----
+    {
+      uint64_t pool_threads = 8192, max_nodes = 131072;
+      if (const char* e = getenv("MAPAD_POOL_THREADS")) pool_threads = strtoull(e, nullptr, 10);
+      if (const char* e = getenv("MAPAD_POOL_MAX_NODES")) max_nodes = strtoull(e, nullptr, 10);
+      const uint64_t hard_max = (uint64_t)MAPAD_POOL_MAX_NODE_CHUNKS << PoolWorkspace<WIDE>::NPC_SHIFT;
+      max_nodes = std::min<uint64_t>(max_nodes, hard_max);
+      const uint64_t n_chunks = h->ws_budget / MAPAD_CHUNK_BYTES;
+      const int tblock = 128;
+      pool_threads = std::min<uint64_t>(pool_threads, n_chunks / 4);       // leave at least half of the pool for growth
+      pool_threads = std::min<uint64_t>(pool_threads, ((uint64_t)n_work + tblock - 1) / tblock * tblock);
+      pool_threads = pool_threads / tblock * tblock;
+      if (pool_threads >= (uint64_t)tblock && max_nodes >= 2 && n_work > 0) {
+        CK(h->d_pool_next.reserve(n_chunks + 2));
+        CK(h->d_pool_tables.reserve(pool_threads * (MAPAD_POOL_MAX_NODE_CHUNKS + MAPAD_POOL_MAX_HEAP_CHUNKS)));
+        CK(h->d_pool_hits.reserve(pool_threads * MAPAD_MAX_HITS));
+        ChunkPool pool;
+        pool.base = h->d_ws.p;
+        pool.n_chunks = (uint32_t)n_chunks;
+        pool.next = h->d_pool_next.p + 2;
+        pool.head = reinterpret_cast<unsigned long long*>(h->d_pool_next.p);
+        k_pool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(pool, (uint32_t)(2 * pool_threads));
+        ++launches;
+        CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));
+        k_search_pool<WIDE><<<(unsigned)(pool_threads / tblock), tblock, 0, h->stream>>>(
+            ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, pool, h->d_pool_tables.p, h->d_pool_hits.p, (uint32_t)max_nodes, work, n_work,
+            deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p, (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
+            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu));
+        ++launches;
+        CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        const uint32_t n_def = h->h_cur.p->n_deferred;
+        work = deferred;
+        deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
+        n_work = n_def;
+        if (!cap_env) cap = std::max<uint64_t>(cap, max_nodes * 16);  // the warp lanes continue above the pool lane's limit
+      }
+    }
     for (int lane = 0; n_work > 0; ++lane) {
       if (cap > full_cap) cap = full_cap;
       uint64_t warps_mem = h->ws_budget / (cap * per_entry);
@@ -489,7 +533,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
       const uint64_t n_wslots = (uint64_t)grid * warps_per_block;
       const size_t heap_bytes = (size_t)n_wslots * cap * sizeof(HeapEnt);
       const size_t node_bytes = (size_t)n_wslots * cap * sizeof(NodeT<WIDE>);
-      CK(h->d_ws.reserve(heap_bytes + node_bytes + 256));
+      CK(h->d_ws.reserve(heap_bytes + node_bytes + 256, true));
       HeapEnt* heap_base = reinterpret_cast<HeapEnt*>(h->d_ws.p);
       NodeT<WIDE>* node_base = reinterpret_cast<NodeT<WIDE>*>(h->d_ws.p + ((heap_bytes + 63) & ~(size_t)63));
       CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter

@@ -214,28 +214,46 @@ struct HitTmp {  // HitInterval before its edit operations are extracted
 #define MAPAD_MAX_HITS 20   // the search returns once len() > 9, one expansion adds at most 9 (mapping.rs:1348)
 #define MAPAD_NO_NODE 0xffffffffu
 
+// Workspace policies.  A workspace provides: node(id) -> NodeT&, ensure_node(id) / ensure_heap(n) (grow or
+// refuse), heap() -> a store with get/set, and the hit array.  `Workspace` is the contiguous per-thread /
+// per-warp arena; PoolWorkspace (search_pool.cuh) grows in fixed-size chunks taken from a shared pool.
+template <bool WIDE>
+struct PlainNodes {
+  NodeT<WIDE>* p;
+  MAPAD_DEV NodeT<WIDE>& node(uint32_t id) const { return p[id]; }
+};
 template <bool WIDE>
 struct Workspace {  // one per persistent thread; lives in global memory
-  HeapEnt* heap;
+  HeapEnt* heap_;
   NodeT<WIDE>* nodes;
   HitTmp* hits;
-  uint32_t cap;   // capacity of heap[] and nodes[]
+  uint32_t cap;   // capacity of heap_[] and nodes[]
+  MAPAD_DEV NodeT<WIDE>& node(uint32_t id) const { return nodes[id]; }
+  MAPAD_DEV bool ensure_node(uint32_t id) { return id < cap; }
+  MAPAD_DEV bool ensure_heap(uint32_t n) { return n < cap; }
+  MAPAD_DEV uint32_t min_cap() const { return cap; }
+  struct Store {
+    HeapEnt* d;
+    MAPAD_DEV HeapEnt get(uint32_t i) const { return d[i]; }
+    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { d[i] = e; }
+  };
+  MAPAD_DEV Store heap() const { return Store{heap_}; }
 };
 
 struct SearchCounters { uint32_t frames_popped, tree_nodes, max_stack, limit_hit; };
 
 template <bool WIDE>
-MAPAD_DEV void node_store(NodeT<WIDE>* nodes, uint32_t id, const Frame& f, uint32_t parent, uint32_t op) {
+MAPAD_DEV void node_store(NodeT<WIDE>& dst, const Frame& f, uint32_t parent, uint32_t op) {
   NodeT<WIDE> n;
   n.parent = parent; n.op = op;
   n.lower = (decltype(n.lower))f.iv.lower; n.lower_rev = (decltype(n.lower))f.iv.lower_rev; n.size = (decltype(n.lower))f.iv.size;
   n.start = (int16_t)f.start; n.len = (int16_t)f.len;
   n.gap_f = (uint8_t)f.gap_f; n.gap_b = (uint8_t)f.gap_b; n.ngaps = (uint8_t)f.ngaps; n.pad0 = 0; n.pad1 = 0;
-  nodes[id] = n;
+  dst = n;
 }
 template <bool WIDE>
-MAPAD_DEV void node_load(const NodeT<WIDE>* nodes, uint32_t id, Frame& f) {
-  NodeT<WIDE> n = nodes[id];
+MAPAD_DEV void node_load(const NodeT<WIDE>& src, uint32_t id, Frame& f) {
+  NodeT<WIDE> n = src;
   f.iv.lower = n.lower; f.iv.lower_rev = n.lower_rev; f.iv.size = n.size;
   f.start = n.start; f.len = n.len;
   f.gap_f = n.gap_f; f.gap_b = n.gap_b; f.ngaps = n.ngaps;
@@ -411,8 +429,8 @@ struct SearchState {
   bool overflow;
 };
 
-template <bool WIDE>
-MAPAD_DEV void check_and_push(const Workspace<WIDE>& ws, SearchState<WIDE>& st, Frame f, uint32_t parent_node, uint32_t op, int L,
+template <bool WIDE, class WS>
+MAPAD_DEV void check_and_push(WS& ws, SearchState<WIDE>& st, Frame f, uint32_t parent_node, uint32_t op, int L,
                               const BoundCtx& bc, const DevParams& P) {
   if (st.n_hits > 0) {
     if (bound_reject_iterative(bc, f.score, ws.hits[0].score)) return;
@@ -422,172 +440,216 @@ MAPAD_DEV void check_and_push(const Workspace<WIDE>& ws, SearchState<WIDE>& st, 
   uint32_t id;
   if (st.free_head != MAPAD_NO_NODE) {
     id = st.free_head;
-    st.free_head = ws.nodes[id].parent;  // vacant entries chain through `parent`
+    st.free_head = ws.node(id).parent;  // vacant entries chain through `parent`
   } else {
     id = st.node_hi;
-    if (id >= ws.cap) { st.overflow = true; return; }
+    if (!ws.ensure_node(id)) { st.overflow = true; return; }
     st.node_hi += 1;
   }
   st.tree_len += 1;
-  node_store<WIDE>(ws.nodes, id, f, parent_node, op);
+  node_store<WIDE>(ws.node(id), f, parent_node, op);
   if (f.len == L) {
     HitTmp h;
     h.score = f.score; h.node = id; h.lower = f.iv.lower; h.lower_rev = f.iv.lower_rev; h.size = f.iv.size;
     if (st.n_hits < MAPAD_MAX_HITS) bh_push(ws.hits, st.n_hits, h);
     return;
   }
-  if (st.heap_n >= ws.cap) { st.overflow = true; return; }
-  mm_push(PlainHeapStore{ws.heap}, st.heap_n, HeapEnt{f.score, id});
+  if (!ws.ensure_heap(st.heap_n)) { st.overflow = true; return; }
+  mm_push(ws.heap(), st.heap_n, HeapEnt{f.score, id});
 }
 
-template <bool WIDE>
-MAPAD_DEV int search_read(const DevIndex& ix, const DevParams& P, const float* bound_table, const uint8_t* seq, int L, int start_pos,
-                          const PenRow* delta, const float* dcomp, const Workspace<WIDE>& ws, SearchState<WIDE>& st,
-                          SearchCounters& ctr) {
-  const BoundCtx bc = bound_ctx(P, bound_table, L);
-  const float open_ext = fadd(P.gap_open, P.gap_extend);
+// One read's constants and one pop-and-expand step of the search.  The thread kernels run
+//   begin; while (step == STEP_CONTINUE);
+// as a FLAT loop in which a thread that finishes a read picks up its next one, so that the 32 reads of a warp
+// stay in the same loop body instead of waiting for the slowest read of a round.
+enum { STEP_CONTINUE = 0, STEP_DONE = 1, STEP_OVERFLOW = 2 };
+struct SearchJob {
+  const uint8_t* seq;
+  const PenRow* delta;
+  const float* dcomp;
+  int L, start_pos;
+  BoundCtx bc;
+  float open_ext;
+};
+MAPAD_DEV SearchJob make_job(const DevParams& P, const float* bound_table, const uint8_t* seq, int L, int start_pos, const PenRow* delta,
+                             const float* dcomp) {
+  SearchJob job;
+  job.seq = seq; job.delta = delta; job.dcomp = dcomp; job.L = L; job.start_pos = start_pos;
+  job.bc = bound_ctx(P, bound_table, L);
+  job.open_ext = fadd(P.gap_open, P.gap_extend);
+  return job;
+}
+
+template <bool WIDE, class WS>
+MAPAD_DEV int search_begin(const DevIndex& ix, const SearchJob& job, WS& ws, SearchState<WIDE>& st, SearchCounters& ctr) {
   st.heap_n = 0; st.node_hi = 0; st.free_head = MAPAD_NO_NODE; st.tree_len = 0; st.n_hits = 0; st.overflow = false;
   ctr.frames_popped = 0; ctr.tree_nodes = 0; ctr.max_stack = 0; ctr.limit_hit = 0;
-  if (ws.cap < 2) return 1;
-  {
-    Frame root;
-    root.iv = BiIv{0, 0, ix.m.n};
-    root.start = start_pos; root.len = 0; root.gap_f = GAP_CLOSED; root.gap_b = GAP_CLOSED; root.ngaps = 0;
-    root.score = 0.0f; root.node = 0;
-    node_store<WIDE>(ws.nodes, 0, root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
-    st.node_hi = 1; st.tree_len = 1;
-    mm_push(PlainHeapStore{ws.heap}, st.heap_n, HeapEnt{0.0f, 0});
-  }
+  if (ws.min_cap() < 2 || !ws.ensure_node(0) || !ws.ensure_heap(0)) return STEP_OVERFLOW;
+  Frame root;
+  root.iv = BiIv{0, 0, ix.m.n};
+  root.start = job.start_pos; root.len = 0; root.gap_f = GAP_CLOSED; root.gap_b = GAP_CLOSED; root.ngaps = 0;
+  root.score = 0.0f; root.node = 0;
+  node_store<WIDE>(ws.node(0), root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
+  st.node_hi = 1; st.tree_len = 1;
+  mm_push(ws.heap(), st.heap_n, HeapEnt{0.0f, 0});
+  return STEP_CONTINUE;
+}
+
+template <bool WIDE, class WS>
+MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJob& job, WS& ws, SearchState<WIDE>& st, SearchCounters& ctr) {
+  const int L = job.L;
+  const BoundCtx& bc = job.bc;
+  const float open_ext = job.open_ext;
   HeapEnt top;
-  while (mm_pop_max(PlainHeapStore{ws.heap}, st.heap_n, top)) {
-    ctr.frames_popped += 1;
-    Frame sf;
-    node_load<WIDE>(ws.nodes, top.node, sf);
-    sf.score = top.score;
-    int j, d_k, d_l;
-    bool forward;
-    if (sf.start <= L - sf.start - sf.len) {  // mapping.rs:1077-1097
-      j = sf.start + sf.len; forward = true; d_k = sf.start; d_l = sf.start + sf.len;
-    } else {
-      j = sf.start - 1; forward = false; d_k = sf.start - 1; d_l = sf.start + sf.len - 1;
+  if (!mm_pop_max(ws.heap(), st.heap_n, top)) { ctr.tree_nodes = st.tree_len; return STEP_DONE; }
+  ctr.frames_popped += 1;
+  Frame sf;
+  node_load<WIDE>(ws.node(top.node), top.node, sf);
+  sf.score = top.score;
+  int j, d_k, d_l;
+  bool forward;
+  if (sf.start <= L - sf.start - sf.len) {  // mapping.rs:1077-1097
+    j = sf.start + sf.len; forward = true; d_k = sf.start; d_l = sf.start + sf.len;
+  } else {
+    j = sf.start - 1; forward = false; d_k = sf.start - 1; d_l = sf.start + sf.len - 1;
+  }
+  const PenRow row = job.delta[j];
+  const int side_gap = forward ? sf.gap_f : sf.gap_b;
+  const float insertion_score = fadd(side_gap == GAP_INS ? P.gap_extend : open_ext, sf.score);
+  const float deletion_score = fadd(side_gap == GAP_DEL ? P.gap_extend : open_ext, sf.score);
+  const int num_gaps_open = side_gap == GAP_CLOSED ? sf.ngaps + 1 : sf.ngaps;
+  const float lower_bound = d_get(job.dcomp, L, job.start_pos, d_k, d_l);
+  if (st.n_hits > 0) {  // mapping.rs:1201-1208
+    if (bound_reject_iterative(bc, fadd(sf.score, lower_bound), ws.hits[0].score)) return STEP_DONE;
+  }
+  const int child_start = forward ? sf.start : sf.start - 1;
+  // The (at most nine) children that pass the static tests are first collected, in the reference's order
+  // (insertion; then for T,G,C,A: deletion, match/mismatch), and then replayed through ONE copy of
+  // check_and_push in a run-time loop: with 32 independent reads per warp this keeps the threads in the same
+  // instructions instead of nine separately predicated copies of the push code.
+  Frame cand[9];
+  uint32_t cand_op[9];
+  int n_cand = 0;
+  // insertion (mapping.rs:1213-1242)
+  {
+    int dist = j < L - j - 1 ? j : L - j - 1;
+    if (!bound_reject(bc, fadd(insertion_score, lower_bound)) && dist >= P.gap_dist_ends) {
+      Frame c = sf;
+      c.start = child_start; c.len = sf.len + 1;
+      if (forward) c.gap_f = GAP_INS; else c.gap_b = GAP_INS;
+      c.score = insertion_score; c.ngaps = num_gaps_open;
+      cand[n_cand] = c; cand_op[n_cand] = pack_op(j, MAPAD_ED_INSERTION, 0); n_cand += 1;
     }
-    const PenRow row = delta[j];
-    const int side_gap = forward ? sf.gap_f : sf.gap_b;
-    const float insertion_score = fadd(side_gap == GAP_INS ? P.gap_extend : open_ext, sf.score);
-    const float deletion_score = fadd(side_gap == GAP_DEL ? P.gap_extend : open_ext, sf.score);
-    const int num_gaps_open = side_gap == GAP_CLOSED ? sf.ngaps + 1 : sf.ngaps;
-    const float lower_bound = d_get(dcomp, L, start_pos, d_k, d_l);
-    if (st.n_hits > 0) {  // mapping.rs:1201-1208
-      if (bound_reject_iterative(bc, fadd(sf.score, lower_bound), ws.hits[0].score)) break;
-    }
-    const int child_start = forward ? sf.start : sf.start - 1;
-    // insertion (mapping.rs:1213-1242)
-    {
-      int dist = j < L - j - 1 ? j : L - j - 1;
-      if (!bound_reject(bc, fadd(insertion_score, lower_bound)) && dist >= P.gap_dist_ends) {
-        Frame c = sf;
-        c.start = child_start; c.len = sf.len + 1;
-        if (forward) c.gap_f = GAP_INS; else c.gap_b = GAP_INS;
-        c.score = insertion_score; c.ngaps = num_gaps_open;
-        check_and_push<WIDE>(ws, st, c, sf.node, pack_op(j, MAPAD_ED_INSERTION, 0), L, bc, P);
-      }
-    }
-    // bidirectional extension (mapping.rs:1245-1339)
-    BiIv ext[4];
-    {
-      BiIv in = forward ? BiIv{sf.iv.lower_rev, sf.iv.lower, sf.iv.size} : sf.iv;
-      extend_all<WIDE>(ix, in, ext);
-    }
-    const bool del_ok = !bound_reject(bc, fadd(deletion_score, lower_bound));
-    const int dist5 = forward ? j : j + 1;
-    const int dist3 = L - dist5;
-    const bool del_dist_ok = (dist5 < dist3 ? dist5 : dist3) >= P.gap_dist_ends;
-    const uint8_t read_base = seq[j];
+  }
+  // bidirectional extension (mapping.rs:1245-1339)
+  BiIv ext[4];
+  {
+    BiIv in = forward ? BiIv{sf.iv.lower_rev, sf.iv.lower, sf.iv.size} : sf.iv;
+    extend_all<WIDE>(ix, in, ext);
+  }
+  const bool del_ok = !bound_reject(bc, fadd(deletion_score, lower_bound));
+  const int dist5 = forward ? j : j + 1;
+  const int dist3 = L - dist5;
+  const bool del_dist_ok = (dist5 < dist3 ? dist5 : dist3) >= P.gap_dist_ends;
+  const uint8_t read_base = job.seq[j];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      BiIv ip = ext[k];
-      if (ip.size < 1) continue;
-      const int rank = 4 - k;
-      uint8_t c;
-      int pen_idx;  // index of the reference base in PenRow
-      if (forward) {
-        ip = BiIv{ip.lower_rev, ip.lower, ip.size};
-        c = complement_base(rank_base(rank));
-        pen_idx = 4 - rank;  // complement: rank r -> 5 - r, index = 4 - r
-      } else {
-        c = rank_base(rank);
-        pen_idx = rank - 1;
-      }
-      if (del_ok && del_dist_ok) {  // deletion (mapping.rs:1265-1302)
-        Frame ch = sf;
-        ch.iv = ip;
-        if (forward) ch.gap_f = GAP_DEL; else ch.gap_b = GAP_DEL;
-        ch.score = deletion_score; ch.ngaps = num_gaps_open;
-        check_and_push<WIDE>(ws, st, ch, sf.node, pack_op(j, MAPAD_ED_DELETION, c), L, bc, P);
-      }
-      const float mm_score = fadd(row.d[pen_idx], sf.score);
-      if (!bound_reject(bc, fadd(mm_score, lower_bound))) {  // match / mismatch (mapping.rs:1307-1338)
-        Frame ch = sf;
-        ch.iv = ip;
-        ch.start = child_start; ch.len = sf.len + 1;
-        if (forward) ch.gap_f = GAP_CLOSED; else ch.gap_b = GAP_CLOSED;
-        ch.score = mm_score;
-        uint32_t op = c == read_base ? pack_op(j, MAPAD_ED_MATCH, 0) : pack_op(j, MAPAD_ED_MISMATCH, c);
-        check_and_push<WIDE>(ws, st, ch, sf.node, op, L, bc, P);
-      }
+  for (int k = 0; k < 4; ++k) {
+    BiIv ip = ext[k];
+    if (ip.size < 1) continue;
+    const int rank = 4 - k;
+    uint8_t c;
+    int pen_idx;  // index of the reference base in PenRow
+    if (forward) {
+      ip = BiIv{ip.lower_rev, ip.lower, ip.size};
+      c = complement_base(rank_base(rank));
+      pen_idx = 4 - rank;  // complement: rank r -> 5 - r, index = 4 - r
+    } else {
+      c = rank_base(rank);
+      pen_idx = rank - 1;
     }
-    if (st.overflow) return 1;
-    if (st.heap_n > ctr.max_stack) ctr.max_stack = st.heap_n;
-    // early exits (mapping.rs:1348-1355)
-    if (st.n_hits > 9 || (st.n_hits > 0 && ws.hits[0].size > 1)) break;
-    // limits (mapping.rs:1358-1380)
-    if (st.heap_n > P.stack_limit || st.tree_len > P.edit_tree_limit) {
-      ctr.limit_hit += 1;
-      if (P.stack_limit_abort) break;
-      long long e1 = (long long)st.heap_n - (long long)P.stack_limit;
-      long long e2 = (long long)st.tree_len - (long long)P.edit_tree_limit;
-      long long excess = e1 > e2 ? e1 : e2;
-      for (long long e = 0; e < excess; ++e) {
-        HeapEnt mn;
-        if (mm_pop_min(PlainHeapStore{ws.heap}, st.heap_n, mn)) {
-          if (mn.node != 0) {  // Tree::remove (backtrack_tree.rs:49-53)
-            ws.nodes[mn.node].parent = st.free_head;
-            st.free_head = mn.node;
-            st.tree_len -= 1;
-          }
+    if (del_ok && del_dist_ok) {  // deletion (mapping.rs:1265-1302)
+      Frame ch = sf;
+      ch.iv = ip;
+      if (forward) ch.gap_f = GAP_DEL; else ch.gap_b = GAP_DEL;
+      ch.score = deletion_score; ch.ngaps = num_gaps_open;
+      cand[n_cand] = ch; cand_op[n_cand] = pack_op(j, MAPAD_ED_DELETION, c); n_cand += 1;
+    }
+    const float mm_score = fadd(row.d[pen_idx], sf.score);
+    if (!bound_reject(bc, fadd(mm_score, lower_bound))) {  // match / mismatch (mapping.rs:1307-1338)
+      Frame ch = sf;
+      ch.iv = ip;
+      ch.start = child_start; ch.len = sf.len + 1;
+      if (forward) ch.gap_f = GAP_CLOSED; else ch.gap_b = GAP_CLOSED;
+      ch.score = mm_score;
+      cand[n_cand] = ch;
+      cand_op[n_cand] = c == read_base ? pack_op(j, MAPAD_ED_MATCH, 0) : pack_op(j, MAPAD_ED_MISMATCH, c);
+      n_cand += 1;
+    }
+  }
+  for (int i = 0; i < n_cand && !st.overflow; ++i) check_and_push<WIDE, WS>(ws, st, cand[i], sf.node, cand_op[i], L, bc, P);
+  if (st.overflow) return STEP_OVERFLOW;
+  if (st.heap_n > ctr.max_stack) ctr.max_stack = st.heap_n;
+  // early exits (mapping.rs:1348-1355)
+  if (st.n_hits > 9 || (st.n_hits > 0 && ws.hits[0].size > 1)) return STEP_DONE;
+  // limits (mapping.rs:1358-1380)
+  if (st.heap_n > P.stack_limit || st.tree_len > P.edit_tree_limit) {
+    ctr.limit_hit += 1;
+    if (P.stack_limit_abort) return STEP_DONE;
+    long long e1 = (long long)st.heap_n - (long long)P.stack_limit;
+    long long e2 = (long long)st.tree_len - (long long)P.edit_tree_limit;
+    long long excess = e1 > e2 ? e1 : e2;
+    for (long long e = 0; e < excess; ++e) {
+      HeapEnt mn;
+      if (mm_pop_min(ws.heap(), st.heap_n, mn)) {
+        if (mn.node != 0) {  // Tree::remove (backtrack_tree.rs:49-53)
+          ws.node(mn.node).parent = st.free_head;
+          st.free_head = mn.node;
+          st.tree_len -= 1;
         }
       }
     }
   }
+  return STEP_CONTINUE;
+}
+
+template <bool WIDE, class WS>
+MAPAD_DEV int search_read(const DevIndex& ix, const DevParams& P, const float* bound_table, const uint8_t* seq, int L, int start_pos,
+                          const PenRow* delta, const float* dcomp, WS& ws, SearchState<WIDE>& st,
+                          SearchCounters& ctr) {
+  const SearchJob job = make_job(P, bound_table, seq, L, start_pos, delta, dcomp);
+  int rc = search_begin<WIDE, WS>(ix, job, ws, st, ctr);
+  while (rc == STEP_CONTINUE) rc = search_step<WIDE, WS>(ix, P, job, ws, st, ctr);
   ctr.tree_nodes = st.tree_len;
-  return 0;
+  return rc == STEP_OVERFLOW ? 1 : 0;
 }
 
 // extract_edit_operations (record.rs:465-500).  For the search order used here the bucket order of
 // the reference collapses to: operations left of the start point in leaf->root order, then the
 // others in root->leaf order.  `out` must hold `total` entries; returns eff_len via reference.
-template <bool WIDE>
-MAPAD_DEV uint32_t path_length(const NodeT<WIDE>* nodes, uint32_t node, int start_pos, uint32_t& n_left) {
+template <bool WIDE, class A>
+MAPAD_DEV uint32_t path_length(const A& nodes, uint32_t node, int start_pos, uint32_t& n_left) {
   uint32_t total = 0;
   n_left = 0;
   while (node != 0) {
-    uint32_t op = nodes[node].op;
+    const NodeT<WIDE>& nd = nodes.node(node);
+    uint32_t op = nd.op;
     total += 1;
     if ((int)(op & 0xffffu) < start_pos) n_left += 1;
-    node = nodes[node].parent;
+    node = nd.parent;
   }
   return total;
 }
-template <bool WIDE>
-MAPAD_DEV void path_write(const NodeT<WIDE>* nodes, uint32_t node, int start_pos, uint32_t total, uint32_t n_left, mapad_edit_op* out) {
+template <bool WIDE, class A>
+MAPAD_DEV void path_write(const A& nodes, uint32_t node, int start_pos, uint32_t total, uint32_t n_left, mapad_edit_op* out) {
   uint32_t li = 0, ri = total;
   (void)n_left;
   while (node != 0) {
-    uint32_t op = nodes[node].op;
+    const NodeT<WIDE>& nd = nodes.node(node);
+    uint32_t op = nd.op;
     mapad_edit_op e;
     e.pos = (uint16_t)(op & 0xffffu); e.kind = (uint8_t)((op >> 16) & 0xffu); e.base = (uint8_t)(op >> 24);
     if ((int)e.pos < start_pos) out[li++] = e; else out[--ri] = e;
-    node = nodes[node].parent;
+    node = nd.parent;
   }
 }
 

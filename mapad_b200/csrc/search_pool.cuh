@@ -1,0 +1,195 @@
+// search_pool.cuh — K2 throughput lane: one read per THREAD (32 independent reads per warp instruction),
+// persistent threads pulling reads from a global queue, workspaces that grow in 64 KiB chunks taken from
+// a shared pool in HBM.  Memory is therefore proportional to what the reads in flight actually need
+// (median read: ~1e3 frames; 99th percentile: ~4e4; the reference sizes every thread for 2e6 frames +
+// 1e7 tree nodes, /root/reference/src/map/mapping.rs:52-54,146-149) and no read is restarted until it
+// outgrows `max_nodes`, at which point it is handed to the warp-cooperative lanes (search_warp.cuh).
+// The search itself is search_core.cuh::search_read — the exact sequential semantics of
+// k_mismatch_search (mapping.rs:1012-1383).
+#pragma once
+#include "search_core.cuh"
+
+namespace mapad {
+
+#define MAPAD_CHUNK_BYTES 65536u
+#define MAPAD_POOL_EMPTY 0xffffffffu
+
+// Treiber stack of free chunk ids; the 32-bit tag in the upper half of `head` defeats ABA.
+struct ChunkPool {
+  uint8_t* base;
+  uint32_t n_chunks;
+  unsigned long long* head;
+  uint32_t* next;
+};
+
+__device__ __forceinline__ uint32_t pool_acquire(const ChunkPool& p) {
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p.head);
+  while (true) {
+    const uint32_t idx = (uint32_t)old;
+    if (idx == MAPAD_POOL_EMPTY) return idx;
+    const uint32_t nxt = reinterpret_cast<volatile uint32_t*>(p.next)[idx];
+    const unsigned long long neu = (((old >> 32) + 1ull) << 32) | nxt;
+    const unsigned long long seen = atomicCAS(p.head, old, neu);
+    if (seen == old) return idx;
+    old = seen;
+  }
+}
+__device__ __forceinline__ void pool_release(const ChunkPool& p, uint32_t idx) {
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p.head);
+  while (true) {
+    reinterpret_cast<volatile uint32_t*>(p.next)[idx] = (uint32_t)old;
+    __threadfence();
+    const unsigned long long neu = (((old >> 32) + 1ull) << 32) | idx;
+    const unsigned long long seen = atomicCAS(p.head, old, neu);
+    if (seen == old) return;
+    old = seen;
+  }
+}
+
+__global__ void k_pool_init(ChunkPool p, uint32_t first_free) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n_chunks) p.next[i] = i + 1 < p.n_chunks ? i + 1 : MAPAD_POOL_EMPTY;
+  if (i == 0) *p.head = first_free < p.n_chunks ? (unsigned long long)first_free : (unsigned long long)MAPAD_POOL_EMPTY;
+}
+
+#define MAPAD_POOL_MAX_NODE_CHUNKS 64
+#define MAPAD_POOL_MAX_HEAP_CHUNKS 16
+
+template <bool WIDE>
+struct PoolWorkspace {
+  static constexpr uint32_t NPC_SHIFT = WIDE ? 10 : 11;              // nodes per chunk: 1024 (48 B) / 2048 (32 B)
+  static constexpr uint32_t HPC_SHIFT = 13;                           // heap entries per chunk: 8192 (8 B)
+  ChunkPool pool;
+  uint32_t* table;       // per thread: [0, 64) node chunks, [64, 80) heap chunks; entry 0 of each is owned for good
+  uint32_t n_node_chunks, n_heap_chunks;
+  HitTmp* hits;
+  uint32_t max_nodes;
+
+  __device__ __forceinline__ NodeT<WIDE>& node(uint32_t id) const {
+    const uint32_t c = table[id >> NPC_SHIFT];
+    return *reinterpret_cast<NodeT<WIDE>*>(pool.base + (size_t)c * MAPAD_CHUNK_BYTES +
+                                           (size_t)(id & ((1u << NPC_SHIFT) - 1u)) * sizeof(NodeT<WIDE>));
+  }
+  __device__ __forceinline__ HeapEnt* heap_slot(uint32_t i) const {
+    const uint32_t c = table[MAPAD_POOL_MAX_NODE_CHUNKS + (i >> HPC_SHIFT)];
+    return reinterpret_cast<HeapEnt*>(pool.base + (size_t)c * MAPAD_CHUNK_BYTES) + (i & ((1u << HPC_SHIFT) - 1u));
+  }
+  __device__ __forceinline__ bool ensure_node(uint32_t id) {
+    if (id >= max_nodes) return false;
+    const uint32_t c = id >> NPC_SHIFT;
+    if (c < n_node_chunks) return true;
+    if (c >= MAPAD_POOL_MAX_NODE_CHUNKS) return false;
+    const uint32_t got = pool_acquire(pool);
+    if (got == MAPAD_POOL_EMPTY) return false;
+    table[c] = got;
+    n_node_chunks = c + 1;
+    return true;
+  }
+  __device__ __forceinline__ bool ensure_heap(uint32_t n) {
+    const uint32_t c = n >> HPC_SHIFT;
+    if (c < n_heap_chunks) return true;
+    if (c >= MAPAD_POOL_MAX_HEAP_CHUNKS) return false;
+    const uint32_t got = pool_acquire(pool);
+    if (got == MAPAD_POOL_EMPTY) return false;
+    table[MAPAD_POOL_MAX_NODE_CHUNKS + c] = got;
+    n_heap_chunks = c + 1;
+    return true;
+  }
+  __device__ __forceinline__ uint32_t min_cap() const { return max_nodes; }
+  __device__ __forceinline__ void release_extra() {  // keep chunk 0 of each kind
+    for (uint32_t c = n_node_chunks; c > 1; --c) pool_release(pool, table[c - 1]);
+    for (uint32_t c = n_heap_chunks; c > 1; --c) pool_release(pool, table[MAPAD_POOL_MAX_NODE_CHUNKS + c - 1]);
+    n_node_chunks = 1;
+    n_heap_chunks = 1;
+  }
+  struct Store {
+    const PoolWorkspace* w;
+    __device__ __forceinline__ HeapEnt get(uint32_t i) const { return *w->heap_slot(i); }
+    __device__ __forceinline__ void set(uint32_t i, HeapEnt e) const { *w->heap_slot(i) = e; }
+  };
+  __device__ __forceinline__ Store heap() const { return Store{this}; }
+};
+
+// Thread slot t owns chunks 2t (nodes) and 2t+1 (heap) permanently; chunks >= 2 * n_threads are pooled.
+template <bool WIDE>
+__global__ void __launch_bounds__(128)
+k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table, const PenRow* __restrict__ delta,
+              const float* __restrict__ dcomp, ChunkPool pool, uint32_t* tables, HitTmp* hit_base, uint32_t max_nodes,
+              const uint32_t* __restrict__ work_list, uint32_t n_work, uint32_t* deferred_list, Cursors* cur, ReadMid* mid,
+              mapad_hit* hit_pool, uint32_t hit_cap, mapad_edit_op* op_pool, uint32_t op_cap) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  PoolWorkspace<WIDE> ws;
+  ws.pool = pool;
+  ws.table = tables + (size_t)slot * (MAPAD_POOL_MAX_NODE_CHUNKS + MAPAD_POOL_MAX_HEAP_CHUNKS);
+  ws.table[0] = 2 * slot;
+  ws.table[MAPAD_POOL_MAX_NODE_CHUNKS] = 2 * slot + 1;
+  ws.n_node_chunks = 1;
+  ws.n_heap_chunks = 1;
+  ws.hits = hit_base + (size_t)slot * MAPAD_MAX_HITS;
+  ws.max_nodes = max_nodes;
+  // Flat loop: every iteration pops and expands ONE frame of the thread's current read; a thread whose read has
+  // finished emits it and picks up the next one in the same iteration, so the warp never waits for a round's slowest read.
+  bool have = false;
+  uint32_t r = 0;
+  int split = 0;
+  SearchJob job;
+  SearchState<WIDE> st;
+  SearchCounters ctr;
+  while (true) {
+    if (!have) {
+      const uint32_t w = atomicAdd(&cur->queue_head, 1u);
+      if (w >= n_work) break;
+      r = work_list ? work_list[w] : w;
+      const uint64_t o = rb.offsets[r];
+      const int L = (int)(rb.offsets[r + 1] - o);
+      if (L <= 0) {
+        ReadMid m;
+        m.n_hits = 0; m.hit_off = 0; m.frames_popped = 0; m.flags = 0;
+        mid[r] = m;
+        continue;
+      }
+      split = alignment_start(P, rb, r, L);
+      job = make_job(P, bound_table, rb.seq + o, L, split, delta + o, dcomp + o);
+      if (search_begin<WIDE>(ix, job, ws, st, ctr) == STEP_OVERFLOW) {
+        deferred_list[atomicAdd(&cur->n_deferred, 1u)] = r;
+        continue;
+      }
+      have = true;
+    }
+    const int rc = search_step<WIDE>(ix, P, job, ws, st, ctr);
+    if (rc == STEP_CONTINUE) continue;
+    have = false;
+    if (rc == STEP_OVERFLOW) {  // outgrew this lane (or the pool ran dry): hand the read to the warp-cooperative lanes
+      ws.release_extra();
+      deferred_list[atomicAdd(&cur->n_deferred, 1u)] = r;
+      continue;
+    }
+    ReadMid m;
+    m.hit_off = 0;
+    m.frames_popped = ctr.frames_popped;
+    m.flags = (ctr.limit_hit ? 1u : 0u) | (work_list ? 2u : 0u);
+    m.n_hits = st.n_hits;
+    if (st.n_hits) {
+      m.hit_off = atomicAdd(&cur->hit_cursor, st.n_hits);
+      for (uint32_t h = 0; h < st.n_hits; ++h) {
+        uint32_t n_left;
+        const uint32_t total = path_length<WIDE>(ws, ws.hits[h].node, split, n_left);
+        const uint32_t op_off = atomicAdd(&cur->op_cursor, total);
+        if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(ws, ws.hits[h].node, split, total, n_left, op_pool + op_off);
+        else atomicOr(&cur->overflow, 1u);
+        if ((uint64_t)m.hit_off + h < hit_cap) {
+          mapad_hit mh;
+          mh.lower = ws.hits[h].lower; mh.lower_rev = ws.hits[h].lower_rev; mh.size = ws.hits[h].size;
+          mh.alignment_score = ws.hits[h].score; mh.edit_off = op_off; mh.edit_len = total; mh.reserved = 0;
+          hit_pool[m.hit_off + h] = mh;
+        } else {
+          atomicOr(&cur->overflow, 1u);
+        }
+      }
+    }
+    ws.release_extra();
+    mid[r] = m;
+  }
+}
+
+}  // namespace mapad

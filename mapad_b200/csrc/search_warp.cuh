@@ -277,7 +277,7 @@ k_search_warp(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
         my_hit_score = sm_hits[lane].score;
         const uint32_t pad = nodes[my_node].pad1;
         total = pad & 0xffffu; n_left = pad >> 16;
-        if (total == 0xffffu || n_left == 0xffffu) total = path_length<WIDE>(nodes, my_node, start_pos, n_left);
+        if (total == 0xffffu || n_left == 0xffffu) total = path_length<WIDE>(PlainNodes<WIDE>{nodes}, my_node, start_pos, n_left);
       }
       uint32_t incl = total;  // inclusive warp scan of `total`
 #pragma unroll
@@ -293,7 +293,7 @@ k_search_warp(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
       m.hit_off = hit_off;
       if ((uint32_t)lane < n_hits) {
         const uint32_t op_off = op_base + (incl - total);
-        if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(nodes, my_node, start_pos, total, n_left, op_pool + op_off);
+        if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(PlainNodes<WIDE>{nodes}, my_node, start_pos, total, n_left, op_pool + op_off);
         else atomicOr(&cur->overflow, 1u);
         if ((uint64_t)hit_off + lane < hit_cap) {
           const NodeT<WIDE> hn = nodes[my_node];

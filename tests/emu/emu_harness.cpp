@@ -81,14 +81,14 @@ int run(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, uint32_t
     rec.n_hits = st.n_hits;
     for (uint32_t h = 0; h < st.n_hits; ++h) {
       uint32_t n_left;
-      uint32_t total = path_length<WIDE>(ws.nodes, ws.hits[h].node, split, n_left);
+      uint32_t total = path_length<WIDE>(ws, ws.hits[h].node, split, n_left);
       mapad_hit mh;
       memset(&mh, 0, sizeof mh);
       mh.lower = ws.hits[h].lower; mh.lower_rev = ws.hits[h].lower_rev; mh.size = ws.hits[h].size;
       mh.alignment_score = ws.hits[h].score;
       mh.edit_off = (uint32_t)out.ops.size(); mh.edit_len = total;
       out.ops.resize(out.ops.size() + total);
-      path_write<WIDE>(ws.nodes, ws.hits[h].node, split, total, n_left, out.ops.data() + mh.edit_off);
+      path_write<WIDE>(ws, ws.hits[h].node, split, total, n_left, out.ops.data() + mh.edit_off);
       out.hits.push_back(mh);
     }
     epilogue_read<WIDE>(ix, P, bp.bound_table.data(), L, in.seeds ? in.seeds[r] : 0u, out.hits.data() + rec.hit_off, rec.n_hits,

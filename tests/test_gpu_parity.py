@@ -160,7 +160,7 @@ print("deferred", int(sum(1 for r in got.records if r["flags"] & 2)), "limit", i
 def test_wide_layout_and_retry_lanes(api):
     """64-bit block layout forced on a small index; tiny first-lane workspace so most reads overflow into
     the retry lanes; results must not change."""
-    out = _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_LANE0_CAP": "64"})
+    out = _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_POOL_MAX_NODES": "64", "MAPAD_LANE0_CAP": "512"})
     assert int(out.split("deferred")[1].split()[0]) > 100, out
 
 
