@@ -260,6 +260,10 @@ void mapad_gpu_destroy(mapad_gpu* h);
 int mapad_gpu_gather_peak(int device, uint64_t table_bytes, uint32_t bytes_per_access, uint64_t n_accesses,
                           double* gbps_out);
 
+/* Test hook: evaluates the device restatements of the glibc float functions the reference reaches through
+ * f32::{log2, exp2, log10} (fn = 0, 1, 2) and compiler-rt's powi (fn = 3, exponent in `iarg`) on `n` host values. */
+int mapad_gpu_debug_libm(int device, int fn, int iarg, uint64_t n, const float* in, float* out);
+
 int mapad_abi_version(void);
 /* sizeof of the ABI PODs, so that bindings can verify their mirrors: 0 params, 1 reads, 2 edit_op, 3 hit, 4 alt,
  * 5 record, 6 results, 7 index_view */

@@ -14,7 +14,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmapad_gpu.so")
+LIB_PATH = os.environ.get("MAPAD_GPU_LIB", os.path.join(_HERE, "libmapad_gpu.so"))  # override only for A/B experiments
 _lib = None
 
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENOMEM", -5: "EINDEX", -6: "EIO", -7: "ELIMIT"}
@@ -60,6 +60,7 @@ def lib():
             "mapad_gpu_last_error": (C.c_char_p, [vp]),
             "mapad_gpu_destroy": (None, [vp]),
             "mapad_gpu_gather_peak": (i32, [i32, u64, u32, u64, P(C.c_double)]),
+            "mapad_gpu_debug_libm": (i32, [i32, i32, i32, u64, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -74,7 +75,7 @@ EXPORTED_SYMBOLS = [
     "mapad_bound_allowed_mismatches", "mapad_index_build", "mapad_index_build_with_draws", "mapad_index_from_view",
     "mapad_index_get_view", "mapad_index_free", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
     "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
-    "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak",
+    "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
 ]
 
 
@@ -281,3 +282,11 @@ def gather_peak(device, table_bytes, bytes_per_access=64, n_accesses=1 << 28):
     out = C.c_double()
     _check(lib().mapad_gpu_gather_peak(device, table_bytes, bytes_per_access, n_accesses, C.byref(out)))
     return float(out.value)
+
+
+def debug_libm(fn, values, iarg=0, device=0):
+    """Device evaluation of the glibc restatements (0 log2f, 1 exp2f, 2 log10f, 3 powi) on a float32 array."""
+    x = np.ascontiguousarray(values, dtype=np.float32)
+    y = np.zeros_like(x)
+    _check(lib().mapad_gpu_debug_libm(device, fn, iarg, len(x), x.ctypes.data, y.ctypes.data))
+    return y

@@ -153,6 +153,20 @@ __global__ void __launch_bounds__(128) k_epilogue(DevIndex ix, DevParams P, Read
   records[r] = rec;
 }
 
+__global__ void k_debug_libm(int fn, int iarg, uint64_t n, const float* __restrict__ in, float* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[i];
+  float y;
+  switch (fn) {
+    case 0: y = emu::log2f_glibc(x); break;
+    case 1: y = emu::exp2f_glibc(x); break;
+    case 2: y = emu::log10f_glibc(x); break;
+    default: y = emu::powi_rt(x, iarg); break;
+  }
+  out[i] = y;
+}
+
 // Roofline denominator: every thread issues independent, uniformly random, `V`*16-byte loads.
 template <int V>
 __global__ void __launch_bounds__(256) k_gather(const uint4* __restrict__ table, uint64_t n_units, uint64_t per_thread, uint64_t seed,
@@ -674,6 +688,22 @@ int mapad_gpu_gather_peak(int device, uint64_t table_bytes, uint32_t bytes_per_a
   cudaFree(table); cudaFree(sink);
   *gbps_out = (double)per_thread * threads * bytes_per_access / (best_ms * 1e-3) / 1e9;
   return MAPAD_OK;
+}
+
+int mapad_gpu_debug_libm(int device, int fn, int iarg, uint64_t n, const float* in, float* out) {
+  if (!in || !out || fn < 0 || fn > 3) return MAPAD_EINVAL;
+  std::string err;
+  int rc = pick_device(device, err);
+  if (rc) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return MAPAD_ECUDA;
+  float *d_in = nullptr, *d_out = nullptr;
+  if (cudaMalloc(&d_in, n * 4 + 4) != cudaSuccess) return MAPAD_ENOMEM;
+  if (cudaMalloc(&d_out, n * 4 + 4) != cudaSuccess) { cudaFree(d_in); return MAPAD_ENOMEM; }
+  cudaMemcpy(d_in, in, n * 4, cudaMemcpyHostToDevice);
+  if (n) k_debug_libm<<<(unsigned)((n + 255) / 256), 256>>>(fn, iarg, n, d_in, d_out);
+  cudaError_t e = cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_in); cudaFree(d_out);
+  return e == cudaSuccess ? MAPAD_OK : MAPAD_ECUDA;
 }
 
 int64_t mapad_format_xa(const mapad_index* index, const mapad_results* res, uint64_t read_idx, char* buf, uint64_t cap) {

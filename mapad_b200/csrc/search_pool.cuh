@@ -111,8 +111,11 @@ struct PoolWorkspace {
 };
 
 // Thread slot t owns chunks 2t (nodes) and 2t+1 (heap) permanently; chunks >= 2 * n_threads are pooled.
+#ifndef MAPAD_POOL_MIN_BLOCKS
+#define MAPAD_POOL_MIN_BLOCKS 4
+#endif
 template <bool WIDE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MAPAD_POOL_MIN_BLOCKS)
 k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table, const PenRow* __restrict__ delta,
               const float* __restrict__ dcomp, ChunkPool pool, uint32_t* tables, HitTmp* hit_base, uint32_t max_nodes,
               const uint32_t* __restrict__ work_list, uint32_t n_work, uint32_t* deferred_list, Cursors* cur, ReadMid* mid,

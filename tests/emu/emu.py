@@ -36,6 +36,7 @@ def lib():
         L.emu_occ4.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.emu_sa_get.restype = C.c_int
         L.emu_sa_get.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.emu_libm_array.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -75,3 +76,10 @@ def sa_get(index, row, layout=-1):
     rc = lib().emu_sa_get(index.h, layout, row, C.byref(out))
     assert rc == 0
     return int(out.value)
+
+
+def libm(fn, values, iarg=0):
+    x = np.ascontiguousarray(values, dtype=np.float32)
+    y = np.zeros_like(x)
+    lib().emu_libm_array(fn, iarg, len(x), x.ctypes.data, y.ctypes.data)
+    return y

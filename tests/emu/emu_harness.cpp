@@ -158,4 +158,15 @@ int emu_sa_get(const mapad_index* index, int layout, uint64_t row, uint64_t* out
   *out = meta.wide ? sa_get<true>(ix, row, steps) : sa_get<false>(ix, row, steps);
   return 0;
 }
+float emu_libm(int fn, int iarg, float x) {
+  switch (fn) {
+    case 0: return emu::log2f_glibc(x);
+    case 1: return emu::exp2f_glibc(x);
+    case 2: return emu::log10f_glibc(x);
+    default: return emu::powi_rt(x, iarg);
+  }
+}
+void emu_libm_array(int fn, int iarg, uint64_t n, const float* in, float* out) {
+  for (uint64_t i = 0; i < n; ++i) out[i] = emu_libm(fn, iarg, in[i]);
+}
 }
