@@ -343,7 +343,7 @@ def main():
         traffic, traffic_src = None, None
         try:  # DRAM bytes per k_search_pool launch from the committed `ncu --set full` capture (profiles/)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            traffic, traffic_src = tj["dram_bytes_per_read"] * args.batch, tj["source"]
         except Exception:
             pass
         # k_search launches of different chunks overlap on the device, so the dominant kernel's achieved rate is taken over
@@ -364,13 +364,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_search_pool (+ k_search_warp for the heavy tail)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": "search = k_search_pool + k_search_warp (99.9 % of device time, profiles/r1_launch_shares.md)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": search_bytes / world / args.steps, "kernel_ms_per_launch_overlapped": search_ms_max / args.steps,
                          "random_gather_peak_64B_gbs": gather, "random_gather_peak_32B_gbs": gather32,
                          "frac_of_gather_peak": (achieved / gather) if gather else None,
-                         "path_algorithmic_gbs": (total_bytes / world) / (dev_ms_max * 1e-3) / 1e9,
-                         "ms_prologue_per_step": prologue_ms / args.steps, "ms_epilogue_per_step": epilogue_ms / args.steps},
+                         "path_algorithmic_gbs": (total_bytes / world) / (dev_ms_max * 1e-3) / 1e9},
         }
         if not args.no_cpu_baseline and world >= 1:
             rps, dt, n, _ = run_cpu(index, spec, batches[args.warmup], args.cpu_sample, threads)
