@@ -130,6 +130,10 @@ typedef struct mapad_index_view {
  * suffix array, BWT, SA sampled every 32 rows.  `sequences[i]` need not be NUL terminated. */
 int mapad_index_build(uint64_t n_contigs, const char* const* names, const char* const* sequences,
                       const uint64_t* lengths, uint64_t seed, mapad_index** out);
+/* Same result, but the suffix sorting runs on CUDA device `device` (prefix-key radix sort; falls back to the host
+ * SA-IS for texts in which two suffixes share a 43-symbol prefix).  Needed for hg19-scale references. */
+int mapad_index_build_on_device(uint64_t n_contigs, const char* const* names, const char* const* sequences,
+                                const uint64_t* lengths, uint64_t seed, int device, mapad_index** out);
 /* Same, but ambiguous symbols in short runs are replaced by the bytes of `replacement_draws`
  * (consumed in text order) — lets tests reproduce a given `mapad index` outcome. */
 int mapad_index_build_with_draws(uint64_t n_contigs, const char* const* names, const char* const* sequences,

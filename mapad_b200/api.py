@@ -44,6 +44,7 @@ def lib():
             "mapad_sdm_representative_mismatch_penalty": (f32, [P(abi.Params)]),
             "mapad_bound_allowed_mismatches": (f32, [P(abi.Params), C.c_size_t]),
             "mapad_index_build": (i32, [u64, P(C.c_char_p), P(C.c_char_p), P(u64), u64, P(vp)]),
+            "mapad_index_build_on_device": (i32, [u64, P(C.c_char_p), P(C.c_char_p), P(u64), u64, i32, P(vp)]),
             "mapad_index_build_with_draws": (i32, [u64, P(C.c_char_p), P(C.c_char_p), P(u64), C.c_char_p, u64, P(vp)]),
             "mapad_index_from_view": (i32, [P(abi.IndexView), P(vp)]),
             "mapad_index_get_view": (i32, [vp, P(abi.IndexView)]),
@@ -72,7 +73,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "mapad_abi_version", "mapad_abi_sizeof", "mapad_params_from_cli", "mapad_sdm_get", "mapad_sdm_representative_mismatch_penalty",
-    "mapad_bound_allowed_mismatches", "mapad_index_build", "mapad_index_build_with_draws", "mapad_index_from_view",
+    "mapad_bound_allowed_mismatches", "mapad_index_build", "mapad_index_build_on_device", "mapad_index_build_with_draws", "mapad_index_from_view",
     "mapad_index_get_view", "mapad_index_free", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
     "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
@@ -117,8 +118,9 @@ class Index:
         self.h = C.c_void_p(handle)
 
     @classmethod
-    def build(cls, contigs, seed=1234, draws=None):
-        """`mapad index` on in-memory contigs: list[(name, sequence)] (src/index/indexing.rs:29-212)."""
+    def build(cls, contigs, seed=1234, draws=None, device=None):
+        """`mapad index` on in-memory contigs: list[(name, sequence)] (src/index/indexing.rs:29-212).
+        device=k: suffix sorting on CUDA device k (required in practice for hg19-scale references)."""
         n = len(contigs)
         names = (C.c_char_p * n)(*[c[0].encode() if isinstance(c[0], str) else c[0] for c in contigs])
         seqs_b = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]
@@ -128,6 +130,8 @@ class Index:
         if draws is not None:
             d = draws.encode() if isinstance(draws, str) else draws
             _check(lib().mapad_index_build_with_draws(n, names, seqs, lens, d, len(d), C.byref(out)))
+        elif device is not None:
+            _check(lib().mapad_index_build_on_device(n, names, seqs, lens, seed, int(device), C.byref(out)))
         else:
             _check(lib().mapad_index_build(n, names, seqs, lens, seed, C.byref(out)))
         return cls(out.value)

@@ -6,9 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmapad_gpu.so")
-SOURCES = ["mapad_gpu.cu", "host_index.cpp", "host_params.cpp", "dev_index_build.cpp"]
+SOURCES = ["mapad_gpu.cu", "gpu_index_build.cu", "host_index.cpp", "host_params.cpp", "dev_index_build.cpp"]
 HEADERS = ["common.h", "dev_index.cuh", "search_core.cuh", "epilogue_core.cuh", "libm_emu.cuh", "host_index.hpp",
-           "host_params.hpp", "dev_index_build.hpp", "sais.hpp", "../../include/mapad_gpu.h"]
+           "host_params.hpp", "dev_index_build.hpp", "sais.hpp", "search_pool.cuh", "search_warp.cuh", "../../include/mapad_gpu.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,232 @@
+// gpu_index_build.cu — suffix sorting on the device for `mapad index`-scale texts (replaces the rust-bio
+// `suffix_array` + `bwt` calls of /root/reference/src/index/indexing.rs:163-166 when the text is too large for
+// the host SA-IS to finish in reasonable time: hg19 scale = 6.2 G symbols).
+//
+// Method: suffixes are bucketed by their first symbol (order: last '$' < first '$' < A < C < G < T < X, as in
+// rust-bio's transform_text) and, inside a bucket, sorted by the following 42 symbols packed 3 bits each into two
+// 63-bit keys (two stable LSD passes of cub::DeviceRadixSort).  Padding past the text end is 0 = the code of the
+// unique last sentinel, so a key pair is ambiguous only if two suffixes share a 43-symbol prefix; that is checked
+// on the device and reported (MAPAD_EINDEX) so the caller can fall back to the host SA-IS — it does not happen for
+// the i.i.d. benchmark genomes (expected number of such pairs at hg19 scale: ~1e-6).  CUB is used as a library
+// for the sort and the scans; index construction is outside the measured hot path.
+#include <cuda_runtime.h>
+
+#include <cub/cub.cuh>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/mapad_gpu.h"
+#include "host_index.hpp"
+
+namespace mapad {
+
+namespace {
+
+#define GK(call)                                                            \
+  do {                                                                      \
+    cudaError_t e_ = (call);                                                \
+    if (e_ != cudaSuccess) {                                                \
+      fprintf(stderr, "gpu_index_build: %s: %s\n", #call, cudaGetErrorString(e_)); \
+      rc = e_ == cudaErrorMemoryAllocation ? MAPAD_ENOMEM : MAPAD_ECUDA;    \
+      goto done;                                                            \
+    }                                                                       \
+  } while (0)
+
+constexpr int TILE = 8192;       // positions per compaction tile
+constexpr int TILE_THREADS = 256;
+
+// rank bytes ($=0 A=1 .. X=5) -> sort codes (last $ = 0, other $ = 1, A..X = 2..6)
+__global__ void k_codes(const uint8_t* __restrict__ ranks, uint8_t* __restrict__ codes, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t r = ranks[i];
+    codes[i] = r == 0 ? (i == n - 1 ? 0 : 1) : (uint8_t)(r + 1);
+  }
+}
+
+__global__ void k_hist(const uint8_t* __restrict__ codes, uint64_t n, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned long long sh[8];
+  if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) loc[codes[i] & 7] += 1;
+  for (int c = 0; c < 8; ++c) if (loc[c]) atomicAdd(&sh[c], loc[c]);
+  __syncthreads();
+  if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_count(const uint8_t* __restrict__ codes, uint64_t n, uint8_t sym,
+                                                              uint32_t* __restrict__ tile_count) {
+  typedef cub::BlockReduce<uint32_t, TILE_THREADS> BR;
+  __shared__ typename BR::TempStorage tmp;
+  const uint64_t base = (uint64_t)blockIdx.x * TILE + (uint64_t)threadIdx.x * (TILE / TILE_THREADS);
+  uint32_t c = 0;
+#pragma unroll 4
+  for (int k = 0; k < TILE / TILE_THREADS; ++k) {
+    const uint64_t i = base + k;
+    if (i < n && codes[i] == sym) c += 1;
+  }
+  const uint32_t tot = BR(tmp).Sum(c);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_write(const uint8_t* __restrict__ codes, uint64_t n, uint8_t sym,
+                                                              const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ pos_out) {
+  typedef cub::BlockScan<uint32_t, TILE_THREADS> BS;
+  __shared__ typename BS::TempStorage tmp;
+  const uint64_t base = (uint64_t)blockIdx.x * TILE + (uint64_t)threadIdx.x * (TILE / TILE_THREADS);
+  uint32_t c = 0;
+#pragma unroll 4
+  for (int k = 0; k < TILE / TILE_THREADS; ++k) {
+    const uint64_t i = base + k;
+    if (i < n && codes[i] == sym) c += 1;
+  }
+  uint32_t off;
+  BS(tmp).ExclusiveSum(c, off);
+  uint64_t w = tile_off[blockIdx.x] + off;
+  for (int k = 0; k < TILE / TILE_THREADS; ++k) {
+    const uint64_t i = base + k;
+    if (i < n && codes[i] == sym) pos_out[w++] = i;
+  }
+}
+
+// key over symbols pos+first .. pos+first+20 (3 bits each, most significant first); past the end: 0
+__device__ __forceinline__ uint64_t make_key(const uint8_t* __restrict__ codes, uint64_t n, uint64_t pos, int first) {
+  uint64_t k = 0;
+#pragma unroll
+  for (int s = 0; s < 21; ++s) {
+    const uint64_t i = pos + first + s;
+    k = (k << 3) | (i < n ? (uint64_t)codes[i] : 0ull);
+  }
+  return k;
+}
+__global__ void k_keys(const uint8_t* __restrict__ codes, uint64_t n, const uint64_t* __restrict__ pos, uint64_t m, int first,
+                       uint64_t* __restrict__ keys) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
+    keys[i] = make_key(codes, n, pos[i], first);
+}
+__global__ void k_ties(const uint8_t* __restrict__ codes, uint64_t n, const uint64_t* __restrict__ pos, uint64_t m,
+                       unsigned long long* __restrict__ ties) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t a = pos[i - 1], b = pos[i];
+    if (make_key(codes, n, a, 1) == make_key(codes, n, b, 1) && make_key(codes, n, a, 22) == make_key(codes, n, b, 22)) atomicAdd(ties, 1ull);
+  }
+}
+
+// BWT + sampled SA + extra rows from a finished SA segment [row0, row0 + m)
+__global__ void k_finish(const uint8_t* __restrict__ ranks, uint64_t n, const uint64_t* __restrict__ sa_seg, uint64_t row0, uint64_t m,
+                         uint32_t rate, uint8_t* __restrict__ bwt, uint64_t* __restrict__ samples, uint64_t* __restrict__ extra,
+                         unsigned int* __restrict__ n_extra) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = row0 + i, p = sa_seg[i];
+    const uint8_t c = p > 0 ? ranks[p - 1] : ranks[n - 1];
+    bwt[row] = c;
+    if (row % rate == 0) samples[row / rate] = p;
+    else if (c == 0) {
+      const unsigned int k = atomicAdd(n_extra, 1u);
+      if (k < 16) { extra[2 * k] = row; extra[2 * k + 1] = p; }
+    }
+  }
+}
+
+}  // namespace
+
+// Fills ix.bwt / ix.sa_sample / ix.extra_rows from the rank-transformed text.
+int gpu_suffix_sort(const std::vector<uint8_t>& ranks, int device, HostIndex& ix) {
+  int rc = MAPAD_OK;
+  const uint64_t n = ranks.size();
+  const uint32_t rate = (uint32_t)ix.sa_rate;
+  uint8_t *d_ranks = nullptr, *d_codes = nullptr, *d_bwt = nullptr;
+  unsigned long long *d_hist = nullptr, *d_ties = nullptr;
+  uint32_t* d_tile_count = nullptr;
+  uint64_t *d_tile_off = nullptr, *d_samples = nullptr, *d_extra = nullptr;
+  uint64_t *d_pos[2] = {nullptr, nullptr}, *d_key[2] = {nullptr, nullptr};
+  unsigned int* d_n_extra = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  const uint64_t n_tiles = (n + TILE - 1) / TILE;
+  const uint64_t n_samples = (n + rate - 1) / rate;
+  unsigned long long hist[8] = {0};
+  uint64_t max_bucket = 0, row0 = 0;
+  const int grid = 148 * 8;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return MAPAD_ENODEV;
+  GK(cudaSetDevice(device));
+  GK(cudaMalloc(&d_ranks, n + 64));
+  GK(cudaMalloc(&d_codes, n + 64));
+  GK(cudaMalloc(&d_bwt, n + 64));
+  GK(cudaMalloc(&d_hist, 64)); GK(cudaMalloc(&d_ties, 8)); GK(cudaMalloc(&d_n_extra, 4));
+  GK(cudaMalloc(&d_tile_count, n_tiles * 4 + 4)); GK(cudaMalloc(&d_tile_off, n_tiles * 8 + 8));
+  GK(cudaMalloc(&d_samples, n_samples * 8 + 8)); GK(cudaMalloc(&d_extra, 16 * 16));
+  GK(cudaMemcpy(d_ranks, ranks.data(), n, cudaMemcpyHostToDevice));
+  GK(cudaMemset(d_hist, 0, 64)); GK(cudaMemset(d_ties, 0, 8)); GK(cudaMemset(d_n_extra, 0, 4));
+  k_codes<<<grid, 256>>>(d_ranks, d_codes, n);
+  k_hist<<<grid, 256>>>(d_codes, n, d_hist);
+  GK(cudaMemcpy(hist, d_hist, 64, cudaMemcpyDeviceToHost));
+  for (int c = 0; c < 8; ++c) max_bucket = hist[c] > max_bucket ? hist[c] : max_bucket;
+  for (int b = 0; b < 2; ++b) { GK(cudaMalloc(&d_pos[b], max_bucket * 8 + 8)); GK(cudaMalloc(&d_key[b], max_bucket * 8 + 8)); }
+  {
+    cub::DoubleBuffer<uint64_t> kb(d_key[0], d_key[1]), vb(d_pos[0], d_pos[1]);
+    size_t need_sort = 0, need_scan = 0;
+    GK(cub::DeviceRadixSort::SortPairs(nullptr, need_sort, kb, vb, (int64_t)max_bucket, 0, 63));
+    GK(cub::DeviceScan::ExclusiveSum(nullptr, need_scan, d_tile_count, d_tile_off, (int64_t)n_tiles));
+    tmp_bytes = need_sort > need_scan ? need_sort : need_scan;
+    GK(cudaMalloc(&d_tmp, tmp_bytes + 256));
+  }
+  for (int sym = 0; sym < 8; ++sym) {
+    const uint64_t m = hist[sym];
+    if (m == 0) continue;
+    // ordered compaction of the positions whose first symbol is `sym`
+    k_tile_count<<<(unsigned)n_tiles, TILE_THREADS>>>(d_codes, n, (uint8_t)sym, d_tile_count);
+    { size_t tb = tmp_bytes; GK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_tile_count, d_tile_off, (int64_t)n_tiles)); }
+    k_tile_write<<<(unsigned)n_tiles, TILE_THREADS>>>(d_codes, n, (uint8_t)sym, d_tile_off, d_pos[0]);
+    uint64_t* sorted = d_pos[0];
+    if (m > 1) {
+      // LSD: symbols 22..42 first, then symbols 1..21 (the radix sort is stable)
+      cub::DoubleBuffer<uint64_t> kb(d_key[0], d_key[1]), vb(d_pos[0], d_pos[1]);
+      k_keys<<<grid, 256>>>(d_codes, n, vb.Current(), m, 22, kb.Current());
+      { size_t tb = tmp_bytes; GK(cub::DeviceRadixSort::SortPairs(d_tmp, tb, kb, vb, (int64_t)m, 0, 63)); }
+      k_keys<<<grid, 256>>>(d_codes, n, vb.Current(), m, 1, kb.Current());
+      { size_t tb = tmp_bytes; GK(cub::DeviceRadixSort::SortPairs(d_tmp, tb, kb, vb, (int64_t)m, 0, 63)); }
+      sorted = vb.Current();
+      k_ties<<<grid, 256>>>(d_codes, n, sorted, m, d_ties);
+    }
+    k_finish<<<grid, 256>>>(d_ranks, n, sorted, row0, m, rate, d_bwt, d_samples, d_extra, d_n_extra);
+    row0 += m;
+  }
+  GK(cudaDeviceSynchronize());
+  {
+    unsigned long long ties = 0;
+    unsigned int n_extra = 0;
+    GK(cudaMemcpy(&ties, d_ties, 8, cudaMemcpyDeviceToHost));
+    GK(cudaMemcpy(&n_extra, d_n_extra, 4, cudaMemcpyDeviceToHost));
+    if (ties != 0 || row0 != n || n_extra > 16) {
+      fprintf(stderr, "gpu_index_build: %llu suffix pairs share a 43-symbol prefix (repetitive text): use the host builder\n", ties);
+      rc = MAPAD_EINDEX;
+      goto done;
+    }
+    ix.bwt.resize(n);
+    ix.sa_sample.resize(n_samples);
+    GK(cudaMemcpy(ix.bwt.data(), d_bwt, n, cudaMemcpyDeviceToHost));
+    GK(cudaMemcpy(ix.sa_sample.data(), d_samples, n_samples * 8, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> ex(2 * (size_t)n_extra);
+    if (n_extra) GK(cudaMemcpy(ex.data(), d_extra, 16 * (size_t)n_extra, cudaMemcpyDeviceToHost));
+    // sort the (row, position) pairs by row (at most two)
+    for (size_t a = 0; a < n_extra; ++a)
+      for (size_t b = a + 1; b < n_extra; ++b)
+        if (ex[2 * b] < ex[2 * a]) { std::swap(ex[2 * a], ex[2 * b]); std::swap(ex[2 * a + 1], ex[2 * b + 1]); }
+    ix.extra_rows = ex;
+  }
+done:
+  cudaFree(d_ranks); cudaFree(d_codes); cudaFree(d_bwt); cudaFree(d_hist); cudaFree(d_ties); cudaFree(d_n_extra);
+  cudaFree(d_tile_count); cudaFree(d_tile_off); cudaFree(d_samples); cudaFree(d_extra);
+  cudaFree(d_pos[0]); cudaFree(d_pos[1]); cudaFree(d_key[0]); cudaFree(d_key[1]); cudaFree(d_tmp);
+  return rc;
+}
+
+struct GpuSaHookInstaller {
+  GpuSaHookInstaller() { g_gpu_suffix_sort = &gpu_suffix_sort; }
+};
+static GpuSaHookInstaller g_install_gpu_sa_hook;
+
+}  // namespace mapad

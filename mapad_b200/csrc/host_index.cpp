@@ -15,6 +15,8 @@
 
 namespace mapad {
 
+GpuSuffixSortFn g_gpu_suffix_sort = nullptr;
+
 static inline uint8_t complement_sym(uint8_t b) {
   switch (b) {
     case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
@@ -102,7 +104,7 @@ static void build_sa_bwt(HostIndex& ix, const std::vector<uint8_t>& ranks) {
 }
 
 int HostIndex::build(uint64_t n_contigs, const char* const* names, const char* const* seqs, const uint64_t* lens,
-                     uint64_t seed, const char* draws, uint64_t n_draws) {
+                     uint64_t seed, const char* draws, uint64_t n_draws, int gpu_device) {
   std::vector<uint8_t> ref;
   uint64_t total = 0;
   for (uint64_t c = 0; c < n_contigs; ++c) total += lens[c];
@@ -162,8 +164,17 @@ int HostIndex::build(uint64_t n_contigs, const char* const* names, const char* c
   ref.clear();
   ref.shrink_to_fit();
   sa_rate = 32;
-  if (n < (1ull << 31)) build_sa_bwt<int32_t>(*this, ranks);
-  else build_sa_bwt<int64_t>(*this, ranks);
+  bool sorted_on_device = false;
+  if (gpu_device >= 0) {
+    if (!g_gpu_suffix_sort) return MAPAD_ENODEV;
+    int rc = g_gpu_suffix_sort(ranks, gpu_device, *this);
+    if (rc == MAPAD_OK) sorted_on_device = true;
+    else if (rc != MAPAD_EINDEX) return rc;
+  }
+  if (!sorted_on_device) {
+    if (n < (1ull << 31)) build_sa_bwt<int32_t>(*this, ranks);
+    else build_sa_bwt<int64_t>(*this, ranks);
+  }
   derive_from_bwt();
   refresh_view();
   return MAPAD_OK;
@@ -194,13 +205,14 @@ using mapad::HostIndex;
 extern "C" {
 
 static int build_common(uint64_t n_contigs, const char* const* names, const char* const* sequences,
-                        const uint64_t* lengths, uint64_t seed, const char* draws, uint64_t n_draws, mapad_index** out) {
+                        const uint64_t* lengths, uint64_t seed, const char* draws, uint64_t n_draws, mapad_index** out,
+                        int gpu_device = -1) {
   if (!out || !sequences || !lengths) return MAPAD_EINVAL;
   *out = nullptr;
   HostIndex* ix = new (std::nothrow) HostIndex();
   if (!ix) return MAPAD_ENOMEM;
   int rc;
-  try { rc = ix->build(n_contigs, names, sequences, lengths, seed, draws, n_draws); }
+  try { rc = ix->build(n_contigs, names, sequences, lengths, seed, draws, n_draws, gpu_device); }
   catch (const std::bad_alloc&) { rc = MAPAD_ENOMEM; }
   catch (...) { rc = MAPAD_EINVAL; }
   if (rc != MAPAD_OK) { delete ix; return rc; }
@@ -211,6 +223,12 @@ static int build_common(uint64_t n_contigs, const char* const* names, const char
 int mapad_index_build(uint64_t n_contigs, const char* const* names, const char* const* sequences, const uint64_t* lengths,
                       uint64_t seed, mapad_index** out) {
   return build_common(n_contigs, names, sequences, lengths, seed, nullptr, 0, out);
+}
+
+int mapad_index_build_on_device(uint64_t n_contigs, const char* const* names, const char* const* sequences,
+                                const uint64_t* lengths, uint64_t seed, int device, mapad_index** out) {
+  if (device < 0) return MAPAD_EINVAL;
+  return build_common(n_contigs, names, sequences, lengths, seed, nullptr, 0, out, device);
 }
 
 int mapad_index_build_with_draws(uint64_t n_contigs, const char* const* names, const char* const* sequences,

@@ -23,11 +23,16 @@ struct HostIndex {
   std::vector<const char*> name_ptrs;
   mapad_index_view view;
 
+  // gpu_device >= 0: suffix sorting on that CUDA device (gpu_index_build.cu), falling back to the host SA-IS
+  // when the text is too repetitive for the device sorter
   int build(uint64_t n_contigs, const char* const* names, const char* const* seqs, const uint64_t* lens, uint64_t seed,
-            const char* draws, uint64_t n_draws);
+            const char* draws, uint64_t n_draws, int gpu_device = -1);
   int from_view(const mapad_index_view& v);
   void derive_from_bwt();
   void refresh_view();
 };
+
+typedef int (*GpuSuffixSortFn)(const std::vector<uint8_t>& ranks, int device, HostIndex& ix);
+extern GpuSuffixSortFn g_gpu_suffix_sort;  // installed by gpu_index_build.cu when it is linked in
 
 }  // namespace mapad

@@ -171,3 +171,21 @@ def test_search_limits_eviction(api):
     assert int(out.split("limit")[1].split()[0]) > 20, out
     out = _run_child(CHILD.replace("SPEC_EXTRA", "spec['limits'] = (300, 700); spec['abort'] = True"), {})
     assert int(out.split("limit")[1].split()[0]) > 20, out
+
+
+def test_device_index_builder_matches_host(api):
+    """mapad_index_build_on_device (prefix-key radix sort on the GPU) must produce exactly the arrays of the host
+    SA-IS builder; a repetitive text makes it fall back to the host builder (still identical)."""
+    for gsize, seed in ((300_000, 7), (65_537, 8)):
+        genome = random_genome(gsize, seed=seed)
+        contigs = [("a", genome[: gsize // 2]), ("b", genome[gsize // 2:])]
+        host = api.Index.build(contigs).arrays()
+        dev = api.Index.build(contigs, device=0).arrays()
+        assert host["n"] == dev["n"] and host["less"] == dev["less"] and host["sentinel_rows"] == dev["sentinel_rows"]
+        assert np.array_equal(host["bwt"], dev["bwt"])
+        assert np.array_equal(host["sa_sample"], dev["sa_sample"])
+        assert np.array_equal(host["extra_rows"], dev["extra_rows"])
+    rep = [("r", "ACGT" * 200 + "N" * 30 + "GATTACA" * 50)]
+    host = api.Index.build(rep).arrays()
+    dev = api.Index.build(rep, device=0).arrays()
+    assert np.array_equal(host["bwt"], dev["bwt"]) and np.array_equal(host["sa_sample"], dev["sa_sample"])
