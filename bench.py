@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — reads mapped / second of the B200 hot path (BASELINE.json metric), per the driver contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3|cfg4]
 
 One "step" = one pass of the hot path (penalties + D array + search + epilogue) over one chunk of
 `--batch` simulated reads (the reference's default --batch_size is 250 000; src/main.rs:229).  Every
@@ -90,7 +90,9 @@ def build_workload(cfg, batch, n_batches, rank, need_index=True):
     genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
     index = None
     if need_index:
-        index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234)
+        # references beyond ~0.5 Gbp are suffix-sorted on the GPU (mapad_index_build_on_device); smaller ones on the host (SA-IS)
+        dev = int(os.environ.get("LOCAL_RANK", "0")) if cfg["genome_bp"] > 500_000_000 else None
+        index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234, device=dev)
     t_index = time.time() - t0
     # at most `distinct` different chunks are simulated (3 s of numpy each); longer runs cycle through them
     distinct = min(n_batches, int(os.environ.get("MAPAD_BENCH_DISTINCT_CHUNKS", "12")))
