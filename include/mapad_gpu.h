@@ -264,6 +264,25 @@ void mapad_gpu_destroy(mapad_gpu* h);
 int mapad_gpu_gather_peak(int device, uint64_t table_bytes, uint32_t bytes_per_access, uint64_t n_accesses,
                           double* gbps_out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Callers and data formats either side of the hot path: FASTQ(.GZ) in, BAM out.
+ * ------------------------------------------------------------------------------------------- */
+/* FASTQ / FASTQ.GZ reader with the Record normalisation of src/map/record.rs:184-215 and the chunking and
+ * bad-record skipping of src/map/input_chunk_reader.rs:176-244. */
+int mapad_fastq_open(const char* path, void** reader_out);
+int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out);
+void mapad_fastq_close(void* reader);
+uint64_t mapad_chunk_view(void* chunk, mapad_reads* reads, const char** names, const uint64_t** name_offsets,
+                          const uint16_t** flags, uint64_t* skipped);
+void mapad_chunk_free(void* chunk);
+/* BAM writer: create_bam_header (src/map/mapping.rs:300-398) and create_bam_record (:722-927) from the per-read
+ * fields of a mapad_results; records are written in input order (mapping.rs:291-293). */
+int mapad_bam_open(const char* path, const mapad_index* index, const char* command_line, const char* read_group_id,
+                   int force_overwrite, void** writer_out);
+int mapad_bam_write_chunk(void* writer, const mapad_index* index, const mapad_reads* reads, const char* names,
+                          const uint64_t* name_offsets, const uint16_t* in_flags, const mapad_results* res);
+int mapad_bam_close(void* writer);
+
 /* Test hook: evaluates the device restatements of the glibc float functions the reference reaches through
  * f32::{log2, exp2, log10} (fn = 0, 1, 2) and compiler-rt's powi (fn = 3, exponent in `iarg`) on `n` host values. */
 int mapad_gpu_debug_libm(int device, int fn, int iarg, uint64_t n, const float* in, float* out);

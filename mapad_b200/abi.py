@@ -257,3 +257,20 @@ def pack_reads(seqs, quals):
     qual = np.frombuffer(b"".join(bytes(bytearray(q)) for q in quals), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
     assert len(seq) == len(qual) == int(offsets[-1])
     return seq, qual, offsets
+
+
+def results_struct(batch_result):
+    """abi.BatchResult (numpy copies) -> (Results struct pointing into them, keepalive list)."""
+    r = Results()
+    recs = np.ascontiguousarray(batch_result.records)
+    hits = np.ascontiguousarray(batch_result.hits)
+    ops = np.ascontiguousarray(batch_result.edit_ops)
+    cig = np.ascontiguousarray(batch_result.cigar, dtype=np.uint32)
+    text = np.frombuffer(batch_result.text, dtype=np.uint8).copy() if len(batch_result.text) else np.zeros(1, np.uint8)
+    r.n_reads = len(recs)
+    r.records = C.cast(recs.ctypes.data, C.POINTER(Record))
+    r.hits = C.cast(hits.ctypes.data, C.POINTER(Hit)); r.n_hits = len(hits)
+    r.edit_ops = C.cast(ops.ctypes.data, C.POINTER(EditOp)); r.n_edit_ops = len(ops)
+    r.cigar = C.cast(cig.ctypes.data, C.POINTER(C.c_uint32)); r.n_cigar = len(cig)
+    r.text = C.cast(text.ctypes.data, C.POINTER(C.c_char)); r.n_text = len(batch_result.text)
+    return r, [recs, hits, ops, cig, text]

@@ -62,6 +62,14 @@ def lib():
             "mapad_gpu_destroy": (None, [vp]),
             "mapad_gpu_gather_peak": (i32, [i32, u64, u32, u64, P(C.c_double)]),
             "mapad_gpu_debug_libm": (i32, [i32, i32, i32, u64, vp, vp]),
+            "mapad_fastq_open": (i32, [C.c_char_p, P(vp)]),
+            "mapad_fastq_next_chunk": (i32, [vp, u64, P(vp)]),
+            "mapad_fastq_close": (None, [vp]),
+            "mapad_chunk_view": (u64, [vp, P(abi.Reads), P(vp), P(vp), P(vp), P(u64)]),
+            "mapad_chunk_free": (None, [vp]),
+            "mapad_bam_open": (i32, [C.c_char_p, vp, C.c_char_p, C.c_char_p, i32, P(vp)]),
+            "mapad_bam_write_chunk": (i32, [vp, vp, P(abi.Reads), vp, vp, vp, P(abi.Results)]),
+            "mapad_bam_close": (i32, [vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -77,6 +85,8 @@ EXPORTED_SYMBOLS = [
     "mapad_index_get_view", "mapad_index_free", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
     "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
+    "mapad_fastq_open", "mapad_fastq_next_chunk", "mapad_fastq_close", "mapad_chunk_view", "mapad_chunk_free", "mapad_bam_open",
+    "mapad_bam_write_chunk", "mapad_bam_close",
 ]
 
 
@@ -294,3 +304,53 @@ def debug_libm(fn, values, iarg=0, device=0):
     y = np.zeros_like(x)
     _check(lib().mapad_gpu_debug_libm(device, fn, iarg, len(x), x.ctypes.data, y.ctypes.data))
     return y
+
+
+class FastqChunks:
+    """Iterates a FASTQ / FASTQ.GZ file in chunks of `batch_size` reads (`--batch_size`, src/main.rs:225-232).
+    Yields (abi.Reads, names_ptr, name_offsets_ptr, flags_ptr, n_reads, chunk_handle); free with .free(handle)."""
+
+    def __init__(self, path, batch_size=250_000):
+        self.r = C.c_void_p()
+        _check(lib().mapad_fastq_open(path.encode(), C.byref(self.r)))
+        self.batch_size = batch_size
+        self.skipped = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        ch = C.c_void_p()
+        _check(lib().mapad_fastq_next_chunk(self.r, self.batch_size, C.byref(ch)))
+        R = abi.Reads()
+        names, noff, flags, skipped = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        n = lib().mapad_chunk_view(ch, C.byref(R), C.byref(names), C.byref(noff), C.byref(flags), C.byref(skipped))
+        self.skipped += int(skipped.value)
+        if n == 0:
+            lib().mapad_chunk_free(ch)
+            raise StopIteration
+        return R, names, noff, flags, int(n), ch
+
+    def free(self, ch):
+        lib().mapad_chunk_free(ch)
+
+    def close(self):
+        if self.r:
+            lib().mapad_fastq_close(self.r)
+            self.r = None
+
+
+class BamWriter:
+    def __init__(self, path, index, command_line="", read_group_id=None, force_overwrite=False):
+        self.w = C.c_void_p()
+        self.index = index
+        _check(lib().mapad_bam_open(path.encode(), index.h, command_line.encode(), read_group_id.encode() if read_group_id else None,
+                                    int(force_overwrite), C.byref(self.w)))
+
+    def write_chunk(self, reads_struct, names, name_offsets, flags, results_struct):
+        _check(lib().mapad_bam_write_chunk(self.w, self.index.h, C.byref(reads_struct), names, name_offsets, flags, C.byref(results_struct)))
+
+    def close(self):
+        if self.w:
+            _check(lib().mapad_bam_close(self.w))
+            self.w = None

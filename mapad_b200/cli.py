@@ -1,0 +1,145 @@
+"""`mapad map`-compatible driver on top of the C ABI: FASTQ / FASTQ.GZ in, BAM out.
+
+    python -m mapad_b200.cli map -r reads.fastq.gz -g genome.fa -o out.bam --library single_stranded \
+        -p 0.03 -f 0.5 -t 0.5 -d 0.02 -s 1.0 -i 0.001 -x 0.5
+
+Flag names and defaults follow /root/reference/src/main.rs:96-300.  Differences in this round: the reference is
+indexed in memory from the FASTA on every run (the seven on-disk index files are a later row), BAM/CRAM input is not
+read, and the per-read XD:f timing tag is not written.  Several chunks are kept in flight (--inflight) so that the
+straggler reads of one chunk overlap with the next; records are written in input order.
+"""
+import argparse
+import ctypes as C
+import queue
+import sys
+import threading
+
+import numpy as np
+
+from . import abi, api
+
+
+def read_fasta(path):
+    contigs, name, parts = [], None, []
+    opener = open
+    if path.endswith(".gz"):
+        import gzip
+        opener = gzip.open
+    with opener(path, "rt") as f:
+        for line in f:
+            if line.startswith(">"):
+                if name is not None:
+                    contigs.append((name, "".join(parts)))
+                name, parts = line[1:].split()[0] if line[1:].split() else "", []
+            else:
+                parts.append(line.strip())
+    if name is not None:
+        contigs.append((name, "".join(parts)))
+    return contigs
+
+
+def build_parser():
+    ap = argparse.ArgumentParser(prog="mapad_b200")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    m = sub.add_parser("map", help="Maps reads to a genome")
+    m.add_argument("-r", "--reads", required=True)
+    m.add_argument("-g", "--reference", required=True, help="FASTA file of the genome")
+    m.add_argument("-o", "--output", required=True)
+    m.add_argument("-p", dest="poisson_prob", type=float, required=True)
+    m.add_argument("--library", choices=["single_stranded", "double_stranded"], required=True)
+    m.add_argument("-f", dest="five_prime_overhang", type=float, required=True)
+    m.add_argument("-t", dest="three_prime_overhang", type=float, default=None)
+    m.add_argument("-d", dest="ds_deamination_rate", type=float, required=True)
+    m.add_argument("-s", dest="ss_deamination_rate", type=float, required=True)
+    m.add_argument("-D", dest="divergence", type=float, default=0.02)
+    m.add_argument("-i", dest="indel_rate", type=float, required=True)
+    m.add_argument("-x", dest="gap_extension_penalty", type=float, default=1.0)
+    m.add_argument("--batch_size", type=int, default=250000)
+    m.add_argument("--ignore_base_quality", action="store_true")
+    m.add_argument("--gap_dist_ends", type=int, default=5)
+    m.add_argument("--max_num_gaps_open", type=int, default=2)
+    m.add_argument("--no_search_limit_recovery", action="store_true")
+    m.add_argument("--force_overwrite", action="store_true")
+    m.add_argument("-R", "--read_group", default=None, help="read group ID added to every record")
+    m.add_argument("--seed", type=int, default=1234)
+    m.add_argument("--device", type=int, default=0)
+    m.add_argument("--inflight", type=int, default=4)
+    return ap
+
+
+def params_from_args(a):
+    if a.library == "single_stranded" and a.three_prime_overhang is None:
+        raise SystemExit("-t is required for --library single_stranded")
+    return api.params_from_cli(library=a.library, p=a.poisson_prob, f=a.five_prime_overhang, t=a.three_prime_overhang or 0.0,
+                               d=a.ds_deamination_rate, s=a.ss_deamination_rate, D=a.divergence, i=a.indel_rate,
+                               x=a.gap_extension_penalty, gap_dist_ends=a.gap_dist_ends, max_num_gaps_open=a.max_num_gaps_open,
+                               ignore_base_quality=a.ignore_base_quality, no_search_limit_recovery=a.no_search_limit_recovery)
+
+
+def run_map(a, argv):
+    params = params_from_args(a)
+    contigs = read_fasta(a.reference)
+    total = sum(len(c[1]) for c in contigs)
+    index = api.Index.build(contigs, seed=a.seed, device=a.device if total > 500_000_000 else None)
+    first = api.Mapper(index, params, device=a.device)
+    mappers = [first] + [first.clone() for _ in range(max(1, a.inflight) - 1)]
+    writer = api.BamWriter(a.output, index, command_line=" ".join(argv), read_group_id=a.read_group, force_overwrite=a.force_overwrite)
+    chunks = api.FastqChunks(a.reads, a.batch_size)
+    rng = np.random.default_rng(a.seed)
+    done = {}
+    lock = threading.Condition()
+    jobs = queue.Queue(maxsize=len(mappers))
+    n_reads = n_mapped = 0
+
+    def worker(mp):
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            k, (R, names, noff, flags, n, ch), seeds = job
+            R.seeds = seeds.ctypes.data
+            res = mp.map_raw(R, 0)
+            # results stay valid until this handle's next call: write them under the ordering lock
+            with lock:
+                while done.get("next", 0) != k:
+                    lock.wait()
+                writer.write_chunk(R, names, noff, flags, res)
+                recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
+                done["mapped"] = done.get("mapped", 0) + int(recs["mapped"].sum())
+                done["reads"] = done.get("reads", 0) + n
+                done["next"] = k + 1
+                lock.notify_all()
+            chunks.free(ch)
+
+    threads = [threading.Thread(target=worker, args=(mp,)) for mp in mappers]
+    for t in threads:
+        t.start()
+    k = 0
+    for item in chunks:
+        seeds = rng.integers(0, 1 << 32, size=item[4], dtype=np.uint64).astype(np.uint32)
+        jobs.put((k, item, seeds))
+        k += 1
+    for _ in threads:
+        jobs.put(None)
+    for t in threads:
+        t.join()
+    writer.close()
+    chunks.close()
+    n_reads, n_mapped = done.get("reads", 0), done.get("mapped", 0)
+    print("mapped %d of %d reads (%d skipped on input)" % (n_mapped, n_reads, chunks.skipped), file=sys.stderr)
+    for mp in mappers[1:]:
+        mp.close()
+    first.close()
+    return 0
+
+
+def main(argv=None):
+    argv = list(sys.argv if argv is None else argv)
+    a = build_parser().parse_args(argv[1:])
+    if a.cmd == "map":
+        return run_map(a, argv)
+    return 2
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -189,3 +189,48 @@ def test_device_index_builder_matches_host(api):
     host = api.Index.build(rep).arrays()
     dev = api.Index.build(rep, device=0).arrays()
     assert np.array_equal(host["bwt"], dev["bwt"]) and np.array_equal(host["sa_sample"], dev["sa_sample"])
+
+
+def test_cli_fastq_to_bam(api, tmp_path):
+    """`python -m mapad_b200.cli map` end to end on the GPU: FASTA + FASTQ.GZ in, BAM out, records in input order and
+    identical to what the oracle decides for every read."""
+    import gzip
+    from bamio import read_bam
+    genome = random_genome(120_000, seed=21)
+    contigs = [("chrA", genome[:50_000]), ("chrB", genome[50_000:])]
+    fa = tmp_path / "g.fa"
+    with open(fa, "w") as f:
+        for n, s in contigs:
+            f.write(">%s test contig\n" % n)
+            for i in range(0, len(s), 70):
+                f.write(s[i:i + 70] + "\n")
+    seqs, quals = simulate_reads(genome, 700, (30, 70), seed=5)
+    fq = tmp_path / "r.fastq.gz"
+    with gzip.open(fq, "wt") as f:
+        for i, (s, q) in enumerate(zip(seqs, quals)):
+            f.write("@read%d\n%s\n+\n%s\n" % (i, s.decode(), bytes(c + 33 for c in q).decode()))
+    out = tmp_path / "o.bam"
+    cmd = [sys.executable, "-m", "mapad_b200.cli", "map", "-r", str(fq), "-g", str(fa), "-o", str(out), "--library", "single_stranded",
+           "-p", "0.03", "-f", "0.5", "-t", "0.5", "-d", "0.02", "-s", "1.0", "-i", "0.001", "-x", "0.5", "--batch_size", "150", "--seed", "99"]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    text, refs, recs = read_bam(str(out))
+    assert [x["name"] for x in recs] == ["read%d" % i for i in range(700)]
+    assert refs == [("chrA", 50_000), ("chrB", 70_000)]
+    # same seeds as the CLI draws (numpy generator seeded with --seed, one draw per read, chunk by chunk)
+    rng = np.random.default_rng(99)
+    seeds = np.concatenate([rng.integers(0, 1 << 32, size=min(150, 700 - k), dtype=np.uint64).astype(np.uint32) for k in range(0, 700, 150)])
+    index = api.Index.build(contigs)
+    oix = oracle_index_from_product(index)
+    spec = cli_params("single_stranded")
+    want = ora.map_batch(oix, oracle_params(spec), seqs, quals, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=False)
+    for i, rec in enumerate(recs):
+        s = want.record_summary(i)
+        if not s["mapped"]:
+            assert rec["flag"] & 4
+            continue
+        assert (rec["ref_id"], rec["pos"], rec["mapq"], rec["cigar"], rec["tags"]["MD"], rec["tags"]["NM"]) == \
+               (s["tid"], s["pos"], s["mapq"], s["cigar"], s["md"], s["nm"]), i
+        assert bool(rec["flag"] & 16) == bool(s["strand"])
+        assert np.float32(rec["tags"]["AS"]) == np.float32(s["AS"])
