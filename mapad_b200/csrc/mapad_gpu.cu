@@ -3,8 +3,9 @@
 // Kernel inventory (SURVEY.md §2 "New sm_100a kernels"):
 //   k_penalties   K1a  penalty rows: SimpleAncientDnaModel::get on the device, optimal scores
 //   k_darray      K1b  BiDArray::new: 15 offset scans per read, one scan per lane of a 16-lane group
-//   k_search      K2   k_mismatch_search: persistent threads, one read per thread, dynamic read queue,
-//                      min-max heap + edit tree in a per-thread HBM workspace, hit extraction
+//   k_search_pool K2   k_mismatch_search, throughput lane (search_pool.cuh): persistent threads, one read per thread in a
+//                      flat loop, dynamic read queue, min-max heap + edit tree in pooled 64 KiB HBM chunks
+//   k_search_warp K2   k_mismatch_search, heavy-tail lanes (search_warp.cuh): one read per warp, heap top in shared memory
 //   k_epilogue    K3   intervals_to_bam: best hit, SA locate, strand / contig, MAPQ, CIGAR / MD / NM, alts
 //   k_gather      roofline denominator: independent random sector gathers
 // There is no CPU fallback: every entry point fails with MAPAD_ENODEV without a CUDA device.
@@ -74,62 +75,6 @@ __global__ void __launch_bounds__(256) k_darray(DevIndex ix, DevParams P, ReadBa
 #pragma unroll
     for (int d = 8; d >= 1; d >>= 1) steps += __shfl_xor_sync(mask, steps, d, 16);
     if (l16 == 0) d_steps[r] = steps;
-  }
-}
-
-template <bool WIDE>
-__global__ void __launch_bounds__(128) k_search(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table,
-                                                const PenRow* __restrict__ delta, const float* __restrict__ dcomp,
-                                                HeapEnt* heap_base, NodeT<WIDE>* node_base, HitTmp* hit_base, uint32_t cap,
-                                                const uint32_t* __restrict__ work_list, uint32_t n_work, uint32_t* deferred_list,
-                                                Cursors* cur, ReadMid* mid, mapad_hit* hit_pool, uint32_t hit_cap,
-                                                mapad_edit_op* op_pool, uint32_t op_cap) {
-  const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Workspace<WIDE> ws;
-  ws.heap_ = heap_base + slot * cap;
-  ws.nodes = node_base + slot * cap;
-  ws.hits = hit_base + slot * MAPAD_MAX_HITS;
-  ws.cap = cap;
-  while (true) {
-    const uint32_t w = atomicAdd(&cur->queue_head, 1u);
-    if (w >= n_work) break;
-    const uint32_t r = work_list ? work_list[w] : w;
-    const uint64_t o = rb.offsets[r];
-    const int L = (int)(rb.offsets[r + 1] - o);
-    ReadMid m;
-    m.n_hits = 0; m.hit_off = 0; m.frames_popped = 0; m.flags = 0;
-    if (L > 0) {
-      const int split = alignment_start(P, rb, r, L);
-      SearchState<WIDE> st;
-      SearchCounters ctr;
-      const int rc = search_read<WIDE>(ix, P, bound_table, rb.seq + o, L, split, delta + o, dcomp + o, ws, st, ctr);
-      if (rc != 0) {  // workspace too small: hand the read to the next lane
-        deferred_list[atomicAdd(&cur->n_deferred, 1u)] = r;
-        continue;
-      }
-      m.frames_popped = ctr.frames_popped;
-      m.flags = (ctr.limit_hit ? 1u : 0u) | (work_list ? 2u : 0u);
-      m.n_hits = st.n_hits;
-      if (st.n_hits) {
-        m.hit_off = atomicAdd(&cur->hit_cursor, st.n_hits);
-        for (uint32_t h = 0; h < st.n_hits; ++h) {
-          uint32_t n_left;
-          const uint32_t total = path_length<WIDE>(ws, ws.hits[h].node, split, n_left);
-          const uint32_t op_off = atomicAdd(&cur->op_cursor, total);
-          if ((uint64_t)op_off + total <= op_cap) path_write<WIDE>(ws, ws.hits[h].node, split, total, n_left, op_pool + op_off);
-          else atomicOr(&cur->overflow, 1u);
-          if ((uint64_t)m.hit_off + h < hit_cap) {
-            mapad_hit mh;
-            mh.lower = ws.hits[h].lower; mh.lower_rev = ws.hits[h].lower_rev; mh.size = ws.hits[h].size;
-            mh.alignment_score = ws.hits[h].score; mh.edit_off = op_off; mh.edit_len = total; mh.reserved = 0;
-            hit_pool[m.hit_off + h] = mh;
-          } else {
-            atomicOr(&cur->overflow, 1u);
-          }
-        }
-      }
-    }
-    mid[r] = m;
   }
 }
 
