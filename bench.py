@@ -373,7 +373,7 @@ def main():
                          "frac_of_gather_peak": (achieved / gather) if gather else None,
                          "path_algorithmic_gbs": (total_bytes / world) / (dev_ms_max * 1e-3) / 1e9},
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             rps, dt, n, _ = run_cpu(index, spec, batches[args.warmup], args.cpu_sample, threads)
             out["cpu_baseline"] = {"value": rps, "unit": "reads/s", "cores": threads, "kind": "port",
                                    "sample": "first %d reads of a timed chunk, %.1f s, C++ restatement of mapAD 0.45.0 (reference binary not buildable: no Rust toolchain)" % (n, dt)}

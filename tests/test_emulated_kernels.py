@@ -111,3 +111,37 @@ def test_simulated_reads(library):
     got = emu.map_batch(index, product_params(spec), seqs, quals, seeds=seeds)
     compare_results(want, got)
     assert sum(int(r["mapped"]) for r in got.records) > 150
+
+
+def test_continuous_bound_and_custom_model():
+    """Continuous mismatch bound (-c/-e, mismatch_bounds.rs:77-121) and a user-supplied SequenceDifferenceModel
+    (callback across the C ABI, host-evaluated penalty table) against the oracle."""
+    import ctypes as C
+    from mapad_b200 import abi
+    genome = random_genome(30000, seed=3)
+    index = api.Index.build([("c", genome)])
+    oix = oracle_index_from_product(index)
+    seqs, quals = simulate_reads(genome, 120, (25, 60), seed=17)
+    seeds = np.arange(len(seqs), dtype=np.uint32)
+    # 1. continuous bound with the aDNA model
+    spec = dict(cli_params("single_stranded"))
+    spec["bound"] = ("continuous", -0.25, 1.0)
+    want = ora.map_batch(oix, oracle_params(spec), seqs, quals, seeds=seeds, n_threads=4, want_hits=True)
+    got = emu.map_batch(index, product_params(spec), seqs, quals, seeds=seeds)
+    compare_results(want, got)
+    assert 0 < sum(int(r["mapped"]) for r in got.records) < len(seqs) + 1
+    # 2. custom model = TestDifferenceModel semantics through the callback, bidirectional start (len / 2)
+    spec2 = dict(model=("test", -1.0, -2.0, 0.0), bound=("test", -5.0, None), gaps=(-4.0, -1.0, 3, 2))
+    P = product_params(spec2)
+    P.model_kind = abi.MODEL_CUSTOM
+
+    @abi.SDM_GET_FN
+    def get(user, i, L, frm, to, q):
+        if frm == ord("C") and to == ord("T"):
+            return -1.0
+        return 0.0 if frm == to else -2.0
+
+    P.custom_get = get
+    want = ora.map_batch(oix, oracle_params(spec2), seqs, quals, seeds=seeds, n_threads=4, want_hits=True)
+    got = emu.map_batch(index, P, seqs, quals, seeds=seeds)
+    compare_results(want, got)

@@ -234,3 +234,57 @@ def test_cli_fastq_to_bam(api, tmp_path):
                (s["tid"], s["pos"], s["mapq"], s["cigar"], s["md"], s["nm"]), i
         assert bool(rec["flag"] & 16) == bool(s["strand"])
         assert np.float32(rec["tags"]["AS"]) == np.float32(s["AS"])
+
+
+def test_full_size_cfg1_properties(api):
+    """BASELINE cfg1 at full size (1 Mbp reference, 100 000 x 50 bp reads): size-independent properties —
+    chunking invariance (one chunk vs seven ragged chunks give identical records), internal consistency of every
+    record (CIGAR query length = read length, NM = edits implied by CIGAR + MD, reference span inside the contig),
+    exact-copy reads map to their origin — plus the oracle on a 4 000-read subset."""
+    import re
+    from mapad_b200 import abi, workloads
+    cfg = workloads.CONFIGS["cfg1"]
+    genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
+    index = api.Index.build(workloads.split_contigs(genome, 1))
+    spec = cli_params("single_stranded")
+    m = api.Mapper(index, product_params(spec))
+    seq, qual, off = workloads.simulate_batch(genome, cfg["n_reads"], cfg["len_range"], seed=cfg["seed"])
+    n = len(off) - 1
+    # plant 500 exact copies (forward strand, quality 40) at known positions
+    rng = np.random.default_rng(1)
+    planted = rng.integers(0, cfg["genome_bp"] - 50, size=500)
+    for k, p in enumerate(planted):
+        seq[int(off[k]):int(off[k + 1])] = genome[p:p + 50]
+        qual[int(off[k]):int(off[k + 1])] = 40
+    seeds = np.arange(n, dtype=np.uint32)
+    whole = m.map_batch(seeds=seeds, packed=(seq, qual, off))
+    cuts = [0, 1, 17, 5000, 5001, 40000, 99999, n]
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sub = (seq[int(off[a]):int(off[b])], qual[int(off[a]):int(off[b])], (off[a:b + 1] - off[a]).astype(np.uint64))
+        parts.append(m.map_batch(seeds=seeds[a:b], packed=sub))
+    from mapad_b200 import sharding
+    merged = sharding.merge_results(parts)
+    compare_results(whole, merged, check_hits=False, label_a="one chunk", label_b="seven chunks")
+    rec = whole.records
+    assert rec["mapped"].mean() > 0.8
+    for k, p in enumerate(planted):
+        assert rec["mapped"][k] and rec["pos"][k] == p and rec["strand"][k] == 0 and rec["nm"][k] == 0, k
+    for i in np.nonzero(rec["mapped"])[0][:20000]:
+        cig = whole.cigar_str(int(rec["cigar_off"][i]), int(rec["cigar_len"][i]))
+        md = whole.md_str(int(rec["md_off"][i]), int(rec["md_len"][i]))
+        ops = [(int(a), b) for a, b in re.findall(r"(\d+)([MID])", cig)]
+        assert sum(a for a, b in ops if b in "MI") == 50, (i, cig)
+        ref_span = sum(a for a, b in ops if b in "MD")
+        assert rec["pos"][i] >= 0 and rec["pos"][i] + ref_span <= cfg["genome_bp"]
+        mism = len(re.findall(r"(?<![\^A-Z])[A-Z]", re.sub(r"\^[A-Z]+", "^", md)))
+        dels = sum(a for a, b in ops if b == "D")
+        ins = sum(a for a, b in ops if b == "I")
+        assert rec["nm"][i] == mism + dels + ins, (i, cig, md, int(rec["nm"][i]))
+    sub_n = 4000
+    oix = oracle_index_from_product(index)
+    sub = (seq[: int(off[sub_n])], qual[: int(off[sub_n])], off[: sub_n + 1])
+    want = ora.map_batch(oix, oracle_params(spec), None, None, seeds=seeds[:sub_n], n_threads=os.cpu_count() or 4, want_hits=True, packed=sub)
+    got = m.map_batch(seeds=seeds[:sub_n], want_hits=True, packed=sub)
+    compare_results(want, got)
+    m.close()
