@@ -282,12 +282,28 @@ MAPAD_DEV void mm_push(const H& d, uint32_t& n, HeapEnt e) {
   bool min_level = mm_on_min_level(i);
   bool climb_max;
   if (i > 0) {
-    uint32_t p = (i - 1) >> 1;
-    HeapEnt pe = d.get(p);
+    // The indices a new element can visit depend only on i: its parent p, then the grandparent chain of i or of p.
+    // The parent and both first grandparents are fetched together, so the common case (stop after the parent and one
+    // grandparent compare) costs one memory latency instead of two dependent ones.
+    const uint32_t p = (i - 1) >> 1;
+    const uint32_t gi = i >= 3 ? (p - 1) >> 1 : MAPAD_NO_NODE;                       // grandparent of i
+    const uint32_t gp = p >= 3 ? (((p - 1) >> 1) - 1) >> 1 : MAPAD_NO_NODE;          // grandparent of p
+    const HeapEnt pe = d.get(p);
+    HeapEnt ge_i = e, ge_p = e;
+    if (gi != MAPAD_NO_NODE) ge_i = d.get(gi);
+    if (gp != MAPAD_NO_NODE) ge_p = d.get(gp);
+    bool moved;
     if (min_level) {
-      if (e.score > pe.score) { d.set(i, pe); i = p; climb_max = true; } else climb_max = false;
+      if (e.score > pe.score) { d.set(i, pe); i = p; climb_max = true; moved = true; } else { climb_max = false; moved = false; }
     } else {
-      if (e.score < pe.score) { d.set(i, pe); i = p; climb_max = false; } else climb_max = true;
+      if (e.score < pe.score) { d.set(i, pe); i = p; climb_max = false; moved = true; } else { climb_max = true; moved = false; }
+    }
+    // first grandparent step from the prefetched values
+    if (i >= 3) {
+      const uint32_t g = moved ? gp : gi;
+      const HeapEnt ge = moved ? ge_p : ge_i;
+      if (climb_max ? (e.score > ge.score) : (e.score < ge.score)) { d.set(i, ge); i = g; }
+      else { d.set(i, e); return; }
     }
   } else {
     climb_max = !min_level;

@@ -65,12 +65,18 @@ struct PoolWorkspace {
   HitTmp* hits;
   uint32_t max_nodes;
 
+  // chunk 0 of each kind is owned for good: its base lives in a register, so the common case (small searches)
+  // needs no table lookup in front of every heap / tree access
+  NodeT<WIDE>* node0;
+  HeapEnt* heap0;
   __device__ __forceinline__ NodeT<WIDE>& node(uint32_t id) const {
+    if (id < (1u << NPC_SHIFT)) return node0[id];
     const uint32_t c = table[id >> NPC_SHIFT];
     return *reinterpret_cast<NodeT<WIDE>*>(pool.base + (size_t)c * MAPAD_CHUNK_BYTES +
                                            (size_t)(id & ((1u << NPC_SHIFT) - 1u)) * sizeof(NodeT<WIDE>));
   }
   __device__ __forceinline__ HeapEnt* heap_slot(uint32_t i) const {
+    if (i < (1u << HPC_SHIFT)) return heap0 + i;
     const uint32_t c = table[MAPAD_POOL_MAX_NODE_CHUNKS + (i >> HPC_SHIFT)];
     return reinterpret_cast<HeapEnt*>(pool.base + (size_t)c * MAPAD_CHUNK_BYTES) + (i & ((1u << HPC_SHIFT) - 1u));
   }
@@ -128,6 +134,8 @@ k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
   ws.table[MAPAD_POOL_MAX_NODE_CHUNKS] = 2 * slot + 1;
   ws.n_node_chunks = 1;
   ws.n_heap_chunks = 1;
+  ws.node0 = reinterpret_cast<NodeT<WIDE>*>(pool.base + (size_t)(2 * slot) * MAPAD_CHUNK_BYTES);
+  ws.heap0 = reinterpret_cast<HeapEnt*>(pool.base + (size_t)(2 * slot + 1) * MAPAD_CHUNK_BYTES);
   ws.hits = hit_base + (size_t)slot * MAPAD_MAX_HITS;
   ws.max_nodes = max_nodes;
   // Flat loop: every iteration pops and expands ONE frame of the thread's current read; a thread whose read has
