@@ -143,6 +143,13 @@ int mapad_index_build_with_draws(uint64_t n_contigs, const char* const* names, c
 int mapad_index_from_view(const mapad_index_view* v, mapad_index** out);
 int mapad_index_get_view(const mapad_index* ix, mapad_index_view* out);
 void mapad_index_free(mapad_index* ix);
+/* The reference's on-disk index: `<prefix>.tbw .tle .toc .trt .tsa .tpi .tos`, each a Snappy frame stream around a
+ * bincode `Item{version: u8 = 5, data}` (writers: src/index/indexing.rs:111-207; readers: src/index/mod.rs:212-239,
+ * src/index/versioned_index.rs:46-56).  `save` writes all seven (uncompressed frame chunks); `load` reads .tbw .tsa
+ * .tpi .tos, validates .tle/.trt against them (ranks are re-derived from the BWT, so .toc is not read) and returns
+ * MAPAD_EINDEX on a version mismatch (Error::IndexVersionMismatch) or inconsistent content, MAPAD_EIO on I/O errors. */
+int mapad_index_save(const mapad_index* ix, const char* prefix);
+int mapad_index_load(const char* prefix, mapad_index** out);
 
 /* ---------------------------------------------------------------------------------------------
  * Batch in / out

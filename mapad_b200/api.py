@@ -49,6 +49,8 @@ def lib():
             "mapad_index_from_view": (i32, [P(abi.IndexView), P(vp)]),
             "mapad_index_get_view": (i32, [vp, P(abi.IndexView)]),
             "mapad_index_free": (None, [vp]),
+            "mapad_index_save": (i32, [vp, C.c_char_p]),
+            "mapad_index_load": (i32, [C.c_char_p, P(vp)]),
             "mapad_format_xa": (C.c_int64, [vp, P(abi.Results), u64, C.c_char_p, u64]),
             "mapad_gpu_create": (i32, [vp, P(abi.Params), i32, P(vp)]),
             "mapad_gpu_index_meta_size": (u64, []),
@@ -82,7 +84,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "mapad_abi_version", "mapad_abi_sizeof", "mapad_params_from_cli", "mapad_sdm_get", "mapad_sdm_representative_mismatch_penalty",
     "mapad_bound_allowed_mismatches", "mapad_index_build", "mapad_index_build_on_device", "mapad_index_build_with_draws", "mapad_index_from_view",
-    "mapad_index_get_view", "mapad_index_free", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
+    "mapad_index_get_view", "mapad_index_free", "mapad_index_save", "mapad_index_load", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
     "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
     "mapad_fastq_open", "mapad_fastq_next_chunk", "mapad_fastq_close", "mapad_chunk_view", "mapad_chunk_free", "mapad_bam_open",
@@ -144,6 +146,17 @@ class Index:
             _check(lib().mapad_index_build_on_device(n, names, seqs, lens, seed, int(device), C.byref(out)))
         else:
             _check(lib().mapad_index_build(n, names, seqs, lens, seed, C.byref(out)))
+        return cls(out.value)
+
+    def save(self, prefix):
+        """Writes `<prefix>.tbw .tle .toc .trt .tsa .tpi .tos` as `mapad index` does (src/index/indexing.rs:111-207)."""
+        _check(lib().mapad_index_save(self.h, os.fsencode(prefix)))
+
+    @classmethod
+    def load(cls, prefix):
+        """Reads the index files next to `prefix` (src/index/mod.rs:212-239)."""
+        out = C.c_void_p()
+        _check(lib().mapad_index_load(os.fsencode(prefix), C.byref(out)))
         return cls(out.value)
 
     def __del__(self):

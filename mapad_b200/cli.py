@@ -3,13 +3,16 @@
     python -m mapad_b200.cli map -r reads.fastq.gz -g genome.fa -o out.bam --library single_stranded \
         -p 0.03 -f 0.5 -t 0.5 -d 0.02 -s 1.0 -i 0.001 -x 0.5
 
-Flag names and defaults follow /root/reference/src/main.rs:96-300.  Differences in this round: the reference is
-indexed in memory from the FASTA on every run (the seven on-disk index files are a later row), BAM/CRAM input is not
-read, and the per-read XD:f timing tag is not written.  Several chunks are kept in flight (--inflight) so that the
+    python -m mapad_b200.cli index -g genome.fa [--seed 1234]      # writes genome.fa.{tbw,tle,toc,trt,tsa,tpi,tos}
+
+Flag names and defaults follow /root/reference/src/main.rs:96-300.  `map` loads the seven index files next to the
+FASTA when they exist (as the reference does) and otherwise indexes the FASTA in memory.  Differences in this round:
+BAM/CRAM input is not read, and the per-read XD:f timing tag is not written.  Several chunks are kept in flight (--inflight) so that the
 straggler reads of one chunk overlap with the next; records are written in input order.
 """
 import argparse
 import ctypes as C
+import os
 import queue
 import sys
 import threading
@@ -64,7 +67,24 @@ def build_parser():
     m.add_argument("--seed", type=int, default=1234)
     m.add_argument("--device", type=int, default=0)
     m.add_argument("--inflight", type=int, default=4)
+    ix = sub.add_parser("index", help="Indexes a genome file")
+    ix.add_argument("-g", "--reference", required=True, help="FASTA file of the genome")
+    ix.add_argument("--seed", type=int, default=1234)
+    ix.add_argument("--device", type=int, default=None, help="sort suffixes on this CUDA device (default: only above 0.5 Gbp)")
     return ap
+
+
+def build_index(path, seed, device):
+    contigs = read_fasta(path)
+    total = sum(len(c[1]) for c in contigs)
+    if device is None and total > 500_000_000:
+        device = 0
+    return api.Index.build(contigs, seed=seed, device=device)
+
+
+def run_index(a):
+    build_index(a.reference, a.seed, a.device).save(a.reference)
+    return 0
 
 
 def params_from_args(a):
@@ -78,9 +98,11 @@ def params_from_args(a):
 
 def run_map(a, argv):
     params = params_from_args(a)
-    contigs = read_fasta(a.reference)
-    total = sum(len(c[1]) for c in contigs)
-    index = api.Index.build(contigs, seed=a.seed, device=a.device if total > 500_000_000 else None)
+    if os.path.exists(a.reference + ".tbw"):
+        index = api.Index.load(a.reference)
+    else:
+        print("no index files next to %s: indexing in memory" % a.reference, file=sys.stderr)
+        index = build_index(a.reference, a.seed, None)
     first = api.Mapper(index, params, device=a.device)
     mappers = [first] + [first.clone() for _ in range(max(1, a.inflight) - 1)]
     writer = api.BamWriter(a.output, index, command_line=" ".join(argv), read_group_id=a.read_group, force_overwrite=a.force_overwrite)
@@ -138,6 +160,8 @@ def main(argv=None):
     a = build_parser().parse_args(argv[1:])
     if a.cmd == "map":
         return run_map(a, argv)
+    if a.cmd == "index":
+        return run_index(a)
     return 2
 
 

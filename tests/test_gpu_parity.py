@@ -213,8 +213,13 @@ def test_cli_fastq_to_bam(api, tmp_path):
     cmd = [sys.executable, "-m", "mapad_b200.cli", "map", "-r", str(fq), "-g", str(fa), "-o", str(out), "--library", "single_stranded",
            "-p", "0.03", "-f", "0.5", "-t", "0.5", "-d", "0.02", "-s", "1.0", "-i", "0.001", "-x", "0.5", "--batch_size", "150", "--seed", "99"]
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # `index` writes the seven index files next to the FASTA; `map` then loads them instead of re-indexing
+    r = subprocess.run([sys.executable, "-m", "mapad_b200.cli", "index", "-g", str(fa)], cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert all(os.path.exists(str(fa) + "." + s) for s in ("tbw", "tle", "toc", "trt", "tsa", "tpi", "tos"))
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
+    assert "indexing in memory" not in r.stderr
     text, refs, recs = read_bam(str(out))
     assert [x["name"] for x in recs] == ["read%d" % i for i in range(700)]
     assert refs == [("chrA", 50_000), ("chrB", 70_000)]
