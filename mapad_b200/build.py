@@ -24,13 +24,16 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, extra=()):
+    """out / extra: build a tuning variant (extra nvcc flags, e.g. -DMAPAD_POOL_MIN_BLOCKS=6) next to the product library;
+    a variant is selected at run time with MAPAD_GPU_LIB=<path>."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES] + ["-lz"]
+    cmd = ([nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] +
+           [os.path.join(CSRC, f) for f in SOURCES] + ["-lz"])
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -194,6 +195,7 @@ struct mapad_gpu {
   DevBuf<uint8_t> d_ws;  // workspace pool shared by all lanes
   DevBuf<uint32_t> d_pool_next, d_pool_tables;
   DevBuf<HitTmp> d_pool_hits;
+  DevBuf<unsigned long long> d_lane_stats;
   DevBuf<mapad_hit> d_hits;
   DevBuf<mapad_edit_op> d_ops;
   DevBuf<uint32_t> d_cigar;
@@ -337,7 +339,7 @@ void mapad_gpu_destroy(mapad_gpu* h) {
   h->d_seq.release(); h->d_qual.release(); h->d_offsets.release(); h->d_seeds.release(); h->d_starts.release();
   h->d_custom.release(); h->d_bound.release(); h->d_qualtab.release(); h->d_dpen.release(); h->d_dcomp.release();
   h->d_delta.release(); h->d_dsteps.release(); h->d_deferred_a.release(); h->d_deferred_b.release(); h->d_mid.release();
-  h->d_cur.release(); h->d_ws.release(); h->d_pool_next.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
+  h->d_cur.release(); h->d_ws.release(); h->d_pool_next.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_lane_stats.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
   h->d_records.release();
   h->h_seq.release(); h->h_qual.release(); h->h_offsets.release(); h->h_seeds.release(); h->h_records.release();
   h->h_hits.release(); h->h_ops.release(); h->h_cigar.release(); h->h_text.release(); h->h_cur.release();
@@ -391,6 +393,20 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
   const uint64_t n = h->n_reads, tb = h->total_bases;
   const DevParams& P = h->prep.dp;
   uint64_t launches = 0;
+  // MAPAD_TRACE=1: host-clock timeline of the lanes of every batch on stderr (tuning aid)
+  static const int trace_level = getenv("MAPAD_TRACE") ? atoi(getenv("MAPAD_TRACE")) : 0;  // 1: timeline, 2: + lane utilisation
+  static const bool trace_on = trace_level > 0;
+  static const bool trace_stats = trace_level > 1;
+  static const auto trace_epoch = std::chrono::steady_clock::now();
+  auto now_s = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - trace_epoch).count(); };
+  double trace_t0 = trace_on ? now_s() : 0.0;
+  auto trace = [&](const char* what, uint64_t n_in, uint64_t n_out, uint64_t cap_) {
+    if (!trace_on) return;
+    const double t1 = now_s();
+    fprintf(stderr, "[mapad trace] handle=%p %s start=%.3f end=%.3f reads=%llu deferred=%llu cap=%llu\n", (void*)h, what, trace_t0, t1,
+            (unsigned long long)n_in, (unsigned long long)n_out, (unsigned long long)cap_);
+    trace_t0 = t1;
+  };
   DevIndex ix{h->meta, h->d_blob};
   ReadBatch rb;
   rb.n_reads = n; rb.seq = h->d_seq.p; rb.qual = h->d_qual.p; rb.offsets = h->d_offsets.p;
@@ -433,26 +449,38 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     uint64_t cap = 65536;
     const char* cap_env = getenv("MAPAD_LANE0_CAP");
     if (cap_env) cap = std::max<uint64_t>(2, strtoull(cap_env, nullptr, 10));
-    const int warps_per_block = 4, block = warps_per_block * 32;  // small blocks: a straggler warp pins little of an SM
-    uint32_t hs = 1408;
     const char* hs_env = getenv("MAPAD_SMEM_HEAP");
-    if (hs_env) hs = (uint32_t)std::min<uint64_t>(3400, std::max<uint64_t>(8, strtoull(hs_env, nullptr, 10)));
-    const size_t smem = (size_t)warps_per_block * ((size_t)hs * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA);
-    CK(cudaFuncSetAttribute(k_search_warp<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ---- throughput lane: one read per THREAD, workspaces grown in 64 KiB chunks from a pool that spans the whole
     //      workspace budget; reads that outgrow `max_nodes` restart in the warp-cooperative lanes below ----
     {
-      uint64_t pool_threads = 8192, max_nodes = 131072;
-      if (const char* e = getenv("MAPAD_POOL_THREADS")) pool_threads = strtoull(e, nullptr, 10);
+      uint64_t pool_threads_env = 8192, max_nodes = 131072;
+      if (const char* e = getenv("MAPAD_POOL_THREADS")) pool_threads_env = strtoull(e, nullptr, 10);
       if (const char* e = getenv("MAPAD_POOL_MAX_NODES")) max_nodes = strtoull(e, nullptr, 10);
       const uint64_t hard_max = (uint64_t)MAPAD_POOL_MAX_NODE_CHUNKS << PoolWorkspace<WIDE>::NPC_SHIFT;
       max_nodes = std::min<uint64_t>(max_nodes, hard_max);
+      // optional earlier stages with smaller caps (MAPAD_POOL_STAGES="8192,32768"): reads that outgrow a stage restart in
+      // the next one, packed densely, so that a stage's stragglers are at most cap / previous-cap times the typical read
+      uint64_t stage_caps[8];
+      int n_stages = 0;
+      if (const char* e = getenv("MAPAD_POOL_STAGES")) {
+        const char* q = e;
+        while (*q && n_stages < 7) {
+          char* end = nullptr;
+          const uint64_t v = strtoull(q, &end, 10);
+          if (end == q) break;
+          if (v >= 2 && v < max_nodes) stage_caps[n_stages++] = v;
+          q = *end == ',' ? end + 1 : end;
+        }
+      }
+      stage_caps[n_stages++] = max_nodes;
       const uint64_t n_chunks = h->ws_budget / MAPAD_CHUNK_BYTES;
       const int tblock = 128;
-      pool_threads = std::min<uint64_t>(pool_threads, n_chunks / 4);       // leave at least half of the pool for growth
-      pool_threads = std::min<uint64_t>(pool_threads, ((uint64_t)n_work + tblock - 1) / tblock * tblock);
-      pool_threads = pool_threads / tblock * tblock;
-      if (pool_threads >= (uint64_t)tblock && max_nodes >= 2 && n_work > 0) {
+      for (int stage = 0; stage < n_stages && n_work > 0; ++stage) {
+        const uint64_t stage_cap = stage_caps[stage];
+        uint64_t pool_threads = std::min<uint64_t>(pool_threads_env, n_chunks / 4);  // leave at least half of the pool for growth
+        pool_threads = std::min<uint64_t>(pool_threads, ((uint64_t)n_work + tblock - 1) / tblock * tblock);
+        pool_threads = pool_threads / tblock * tblock;
+        if (pool_threads < (uint64_t)tblock || stage_cap < 2) break;
         CK(h->d_pool_next.reserve(n_chunks + 2));
         CK(h->d_pool_tables.reserve(pool_threads * (MAPAD_POOL_MAX_NODE_CHUNKS + MAPAD_POOL_MAX_HEAP_CHUNKS)));
         CK(h->d_pool_hits.reserve(pool_threads * MAPAD_MAX_HITS));
@@ -464,23 +492,42 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
         k_pool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(pool, (uint32_t)(2 * pool_threads));
         ++launches;
         CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));
+        if (trace_stats) { CK(h->d_lane_stats.reserve(2)); CK(cudaMemsetAsync(h->d_lane_stats.p, 0, 16, h->stream)); }
         k_search_pool<WIDE><<<(unsigned)(pool_threads / tblock), tblock, 0, h->stream>>>(
-            ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, pool, h->d_pool_tables.p, h->d_pool_hits.p, (uint32_t)max_nodes, work, n_work,
+            ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, pool, h->d_pool_tables.p, h->d_pool_hits.p, (uint32_t)stage_cap, work, n_work,
             deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p, (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
-            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu));
+            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu), trace_stats ? h->d_lane_stats.p : nullptr);
         ++launches;
         CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
         const uint32_t n_def = h->h_cur.p->n_deferred;
+        trace("pool", n_work, n_def, stage_cap);
+        if (trace_stats) {
+          unsigned long long ls[2] = {0, 0};
+          CK(cudaMemcpyAsync(ls, h->d_lane_stats.p, 16, cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaStreamSynchronize(h->stream));
+          fprintf(stderr, "[mapad trace] handle=%p pool lane utilisation %.3f (threads=%llu)\n", (void*)h, ls[1] ? (double)ls[0] / (double)ls[1] : 0.0,
+                  (unsigned long long)pool_threads);
+        }
         work = deferred;
         deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
         n_work = n_def;
-        if (!cap_env) cap = std::max<uint64_t>(cap, max_nodes * 16);  // the warp lanes continue above the pool lane's limit
+        if (!cap_env) cap = std::max<uint64_t>(cap, stage_cap * 16);  // the warp lanes continue above the pool lane's limit
       }
     }
     for (int lane = 0; n_work > 0; ++lane) {
       if (cap > full_cap) cap = full_cap;
+      // 4 warps per block, 1408 heap entries per warp in shared memory, up to 4 blocks per SM.  (A one-warp-per-block shape
+      // with ~200 KB of heap on chip was measured and dropped: with many handles in flight its blocks monopolise SMs.)
+      const int warps_per_block = 4, block = warps_per_block * 32;
+      uint32_t hs = 1408;
+      if (hs_env) hs = (uint32_t)std::min<uint64_t>(3400, std::max<uint64_t>(8, strtoull(hs_env, nullptr, 10)));
+      const size_t smem = (size_t)warps_per_block * ((size_t)hs * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA);
+      // the attribute is per function, not per launch: always ask for the largest shape so that handles running in
+      // other host threads never lower it under a pending launch
+      CK(cudaFuncSetAttribute(k_search_warp<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(4 * (3400u * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA))));
       uint64_t warps_mem = h->ws_budget / (cap * per_entry);
       uint64_t warps = std::min<uint64_t>(warps_mem, (uint64_t)h->n_sm * 16);
       warps = std::min<uint64_t>(warps, ((uint64_t)n_work + warps_per_block - 1) / warps_per_block * warps_per_block);
@@ -505,6 +552,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
       CK(cudaStreamSynchronize(h->stream));
       CK(cudaGetLastError());
       const uint32_t n_def = h->h_cur.p->n_deferred;
+      trace("warp", n_work, n_def, cap);
       if (n_def == 0) break;
       if (cap >= full_cap) { h->err = "read exceeded the full-size search workspace"; return MAPAD_ELIMIT; }
       work = deferred;
@@ -531,6 +579,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    trace("epilogue", n, 0, 0);
     const Cursors c = *h->h_cur.p;
     const bool over = c.hit_cursor > h->d_hits.cap || c.op_cursor > h->d_ops.cap || c.cigar_cursor > h->d_cigar.cap ||
                       c.text_cursor > h->d_text.cap || (c.overflow & 1u) || c.pad;

@@ -344,8 +344,9 @@ MAPAD_DEV void mm_trickle_down(const H& d, uint32_t n, uint32_t i) {
     d.set(i, be);
     i = best;
     if (was_child) break;
-    uint32_t p = (i - 1) >> 1;
-    HeapEnt pe = d.get(p);
+    // the parent of the chosen grandchild is one of the two children fetched above (nothing wrote to it since)
+    const uint32_t p = (i - 1) >> 1;
+    const HeapEnt pe = (best - g1) < 2u ? x[0] : x[1];
     if (MAX ? (pe.score > e.score) : (pe.score < e.score)) { d.set(p, e); e = pe; }
   }
   d.set(i, e);

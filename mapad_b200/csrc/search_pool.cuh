@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(128, MAPAD_POOL_MIN_BLOCKS)
 k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table, const PenRow* __restrict__ delta,
               const float* __restrict__ dcomp, ChunkPool pool, uint32_t* tables, HitTmp* hit_base, uint32_t max_nodes,
               const uint32_t* __restrict__ work_list, uint32_t n_work, uint32_t* deferred_list, Cursors* cur, ReadMid* mid,
-              mapad_hit* hit_pool, uint32_t hit_cap, mapad_edit_op* op_pool, uint32_t op_cap) {
+              mapad_hit* hit_pool, uint32_t hit_cap, mapad_edit_op* op_pool, uint32_t op_cap, unsigned long long* lane_stats) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t busy_iters = 0;
   PoolWorkspace<WIDE> ws;
   ws.pool = pool;
   ws.table = tables + (size_t)slot * (MAPAD_POOL_MAX_NODE_CHUNKS + MAPAD_POOL_MAX_HEAP_CHUNKS);
@@ -168,6 +169,7 @@ k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
       have = true;
     }
     const int rc = search_step<WIDE>(ix, P, job, ws, st, ctr);
+    busy_iters += 1;
     if (rc == STEP_CONTINUE) continue;
     have = false;
     if (rc == STEP_OVERFLOW) {  // outgrew this lane (or the pool ran dry): hand the read to the warp-cooperative lanes
@@ -200,6 +202,12 @@ k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
     }
     ws.release_extra();
     mid[r] = m;
+  }
+  if (lane_stats) {  // tuning aid: lane utilisation = sum of the lanes' expansions / (32 x the warp's longest lane)
+    __syncwarp();
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, busy_iters);
+    const uint32_t sm = __reduce_add_sync(0xffffffffu, busy_iters);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&lane_stats[0], (unsigned long long)sm); atomicAdd(&lane_stats[1], 32ull * mx); }
   }
 }
 

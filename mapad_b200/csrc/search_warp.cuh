@@ -39,6 +39,115 @@ __device__ __forceinline__ void hit_push(HitEnt* d, uint32_t& n, HitEnt x) {  //
   n += 1;
 }
 
+// MinMaxHeap::push by the whole warp (same result as search_core.cuh::mm_push).  The positions a new element can
+// visit depend only on its index i: its parent p, then the grandparent chain of i (element stays on its level) or of p
+// (element swapped with the parent).  Lane 0 fetches the parent, lanes 1..15 the chain of i, lanes 16..30 the chain
+// of p — one memory latency for the whole bubble-up instead of one per level — a ballot finds where the climb stops,
+// and the lanes whose ancestors move down write them in parallel.  `n` and `e` must be warp-uniform.
+__device__ __forceinline__ void mm_push_warp(const SplitHeapStore& d, uint32_t& n, HeapEnt e, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const uint32_t i = n;
+  n += 1;
+  if (i == 0) {
+    if (lane == 0) d.set(0, e);
+    __syncwarp();
+    return;
+  }
+  const uint32_t p = (i - 1) >> 1;
+  const bool min_level = mm_on_min_level(i);
+  const bool in_a = lane >= 1 && lane <= 15;
+  const bool in_b = lane >= 16 && lane <= 30;
+  const uint32_t lvl = in_a ? (uint32_t)lane : (in_b ? (uint32_t)(lane - 15) : 0u);   // 1-based level in the chain
+  const uint32_t base1 = (in_b ? p : i) + 1u;                                          // 1-based heap index of the chain's origin
+  const uint32_t anc1 = lvl ? base1 >> (2u * lvl) : 0u;                                // 1-based index of the lvl-th grandparent
+  const bool valid = lvl != 0 && anc1 >= 1u;
+  HeapEnt v = e;
+  if (lane == 0) v = d.get(p);
+  else if (valid) v = d.get(anc1 - 1u);
+  const float pscore = __shfl_sync(FULL, v.score, 0);
+  const uint32_t pnode = __shfl_sync(FULL, v.node, 0);
+  const bool moved = min_level ? (e.score > pscore) : (e.score < pscore);
+  const bool climb_max = min_level == moved;
+  const bool wins = valid && (climb_max ? (e.score > v.score) : (e.score < v.score));
+  const unsigned ball = __ballot_sync(FULL, wins);
+  const unsigned chain = moved ? ((ball >> 16) & 0x7fffu) : ((ball >> 1) & 0x7fffu);
+  const uint32_t t = (uint32_t)__ffs((int)~chain) - 1u;                                // leading run of winning levels
+  const uint32_t cur = moved ? p : i;
+  if (lane == 0) {
+    if (moved) d.set(i, HeapEnt{pscore, pnode});
+    const uint32_t fin = t == 0 ? cur : ((cur + 1u) >> (2u * t)) - 1u;
+    d.set(fin, e);
+  } else if (valid && (moved ? in_b : in_a) && lvl <= t) {
+    const uint32_t below = lvl == 1 ? cur : (base1 >> (2u * (lvl - 1u))) - 1u;          // this ancestor moves one chain level down
+    d.set(below, v);
+  }
+  __syncwarp();
+}
+
+// One level of MinMaxHeap::trickle_down at position i with the six candidates (2 children, 4 grandchildren) already in
+// registers; same decisions as search_core.cuh::mm_trickle_down.  Returns true when the descent continues from the
+// chosen grandchild (then `b` = which of the four).  Warp-uniform; lane 0 writes.
+template <bool MAX>
+__device__ __forceinline__ bool mm_trickle_level(const SplitHeapStore& d, uint32_t n, uint32_t& i, HeapEnt& e, const HeapEnt (&x)[6], int lane,
+                                                 uint32_t& b) {
+  const uint32_t c1 = 2 * i + 1, g1 = 4 * i + 3;
+  uint32_t best = MAPAD_NO_NODE;
+  float bk = e.score;
+  HeapEnt be = e;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    const uint32_t idx = c < 2 ? c1 + c : g1 + (c - 2);
+    if (idx < n && (MAX ? (x[c].score > bk) : (x[c].score < bk))) { best = idx; bk = x[c].score; be = x[c]; }
+  }
+  if (best == MAPAD_NO_NODE) return false;
+  const bool was_child = best <= c1 + 1;
+  if (lane == 0) d.set(i, be);
+  i = best;
+  if (was_child) return false;
+  b = best - g1;
+  const uint32_t p = (i - 1) >> 1;
+  const HeapEnt pe = b < 2u ? x[0] : x[1];
+  if (MAX ? (pe.score > e.score) : (pe.score < e.score)) {
+    if (lane == 0) d.set(p, e);
+    e = pe;
+  }
+  return true;
+}
+
+// MinMaxHeap::trickle_down by the whole warp.  The descent is a chain of dependent loads, one per level, and the deep
+// levels of a large heap live in HBM/L2: lanes 0..29 therefore fetch the whole four-level subtree below the current
+// position at once (2 + 4 + 8 + 16 entries), which covers the candidates of this level AND of the next one whichever
+// grandchild is chosen — two levels per memory latency instead of one.
+template <bool MAX>
+__device__ __forceinline__ void mm_trickle_down_warp(const SplitHeapStore& d, uint32_t n, uint32_t i, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  HeapEnt e = d.get(i);
+  const uint32_t depth = lane < 2 ? 1u : (lane < 6 ? 2u : (lane < 14 ? 3u : 4u));
+  const uint32_t off = lane < 2 ? (uint32_t)lane : (lane < 6 ? (uint32_t)lane - 2u : (lane < 14 ? (uint32_t)lane - 6u : (uint32_t)lane - 14u));
+  while (true) {
+    if (2 * i + 1 >= n) break;
+    const uint32_t idx = ((i + 1u) << depth) - 1u + off;
+    HeapEnt v = e;
+    if (lane < 30 && idx < n) v = d.get(idx);
+    HeapEnt x[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { x[c].score = __shfl_sync(FULL, v.score, c); x[c].node = __shfl_sync(FULL, v.node, c); }
+    uint32_t b = 0;
+    if (!mm_trickle_level<MAX>(d, n, i, e, x, lane, b)) break;
+    if (2 * i + 1 >= n) break;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const int src = c < 2 ? 6 + 2 * (int)b + c : 14 + 4 * (int)b + (c - 2);
+      x[c].score = __shfl_sync(FULL, v.score, src);
+      x[c].node = __shfl_sync(FULL, v.node, src);
+    }
+    if (!mm_trickle_level<MAX>(d, n, i, e, x, lane, b)) break;
+    __syncwarp();  // lane 0's writes of these two levels precede the next fetch
+  }
+  if (lane == 0) d.set(i, e);
+  __syncwarp();
+}
+
 template <bool WIDE>
 __device__ __forceinline__ void node_store_w(NodeT<WIDE>* nodes, uint32_t id, const BiIv& iv, int start, int len, int gap_f, int gap_b,
                                              int ngaps, uint32_t parent, uint32_t op, uint32_t depth, uint32_t nleft) {
@@ -127,11 +236,13 @@ k_search_warp(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
       const float lower_bound = d_get(dc, L, start_pos, d_k, d_l);
       // ---- ... while lane 0 repairs the heap (MinMaxHeap::pop_max: move the last element into the hole, trickle down) ----
       __syncwarp();
-      if (lane == 0) {
+      {
         const uint32_t n1 = heap_n - 1;
         if (mi < n1) {
-          heap.set(mi, heap.get(n1));
-          mm_trickle_down<true>(heap, n1, mi);
+          const HeapEnt last = heap.get(n1);
+          if (lane == 0) heap.set(mi, last);
+          __syncwarp();
+          mm_trickle_down_warp<true>(heap, n1, mi, lane);
         }
       }
       heap_n -= 1;
@@ -195,8 +306,9 @@ k_search_warp(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
       for (int q = 0; q < 9; ++q) sc[q] = __shfl_sync(FULL, my_score, q);
       const bool grows = f_len + 1 == L;  // insertion / match children complete the read
       const uint32_t hits_before = n_hits;
-      // ---- lane 0: replay the accepted children against the sequential heaps (check_and_push_stack_frame) ----
-      if (lane == 0 && mask) {
+      // ---- replay the accepted children in the reference order against the sequential heaps (check_and_push_stack_frame):
+      //      every lane keeps the same copy of the sequential state, memory is written by lane 0, the heap push is cooperative ----
+      if (mask) {
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
           if (!((mask >> q) & 1u)) continue;
@@ -210,24 +322,22 @@ k_search_warp(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
             node_hi += 1;
           }
           tree_len += 1;
-          sm_ids[q] = id;
+          if (lane == 0) sm_ids[q] = id;
           const bool is_deletion = q >= 1 && ((q - 1) & 1) == 0;
           if (grows && !is_deletion) {
-            if (n_hits < MAPAD_MAX_HITS) hit_push(sm_hits, n_hits, HitEnt{s, id});
+            if (n_hits < MAPAD_MAX_HITS) {
+              uint32_t nh = n_hits;
+              if (lane == 0) hit_push(sm_hits, nh, HitEnt{s, id});
+              n_hits += 1;
+              __syncwarp();
+            }
           } else {
             if (heap_n >= cap) { overflow = true; mask &= (1u << q) - 1u; break; }
-            mm_push(heap, heap_n, HeapEnt{s, id});
+            mm_push_warp(heap, heap_n, HeapEnt{s, id}, lane);
           }
         }
       }
       __syncwarp();
-      mask = __shfl_sync(FULL, mask, 0);
-      heap_n = __shfl_sync(FULL, heap_n, 0);
-      node_hi = __shfl_sync(FULL, node_hi, 0);
-      free_head = __shfl_sync(FULL, free_head, 0);
-      tree_len = __shfl_sync(FULL, tree_len, 0);
-      n_hits = __shfl_sync(FULL, n_hits, 0);
-      overflow = __shfl_sync(FULL, overflow ? 1 : 0, 0) != 0;
       // ---- accepted lanes store their nodes ----
       if (lane < 9 && ((mask >> lane) & 1u)) {
         const uint32_t left = (int)(my_op & 0xffffu) < start_pos ? 1u : 0u;
@@ -243,21 +353,29 @@ k_search_warp(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
       if (heap_n > P.stack_limit || tree_len > P.edit_tree_limit) {
         limit_hit += 1;
         if (P.stack_limit_abort) break;
-        if (lane == 0) {
+        {  // MinMaxHeap::pop_min x excess, every lane keeping the same state (lane 0 writes, the descent is cooperative)
           long long e1 = (long long)heap_n - (long long)P.stack_limit;
           long long e2 = (long long)tree_len - (long long)P.edit_tree_limit;
           long long excess = e1 > e2 ? e1 : e2;
-          for (long long e = 0; e < excess; ++e) {
-            HeapEnt mn;
-            if (mm_pop_min(heap, heap_n, mn)) {
-              if (mn.node != 0) { nodes[mn.node].parent = free_head; free_head = mn.node; tree_len -= 1; }
+          for (long long e = 0; e < excess && heap_n > 0; ++e) {
+            const HeapEnt lastv = heap.get(heap_n - 1);
+            heap_n -= 1;
+            HeapEnt mn = lastv;
+            if (heap_n > 0) {
+              mn = heap.get(0);
+              __syncwarp();
+              if (lane == 0) heap.set(0, lastv);
+              __syncwarp();
+              mm_trickle_down_warp<false>(heap, heap_n, 0, lane);
+            }
+            if (mn.node != 0) {  // Tree::remove (backtrack_tree.rs:49-53)
+              if (lane == 0) nodes[mn.node].parent = free_head;
+              free_head = mn.node;
+              tree_len -= 1;
             }
           }
         }
         __syncwarp();
-        heap_n = __shfl_sync(FULL, heap_n, 0);
-        free_head = __shfl_sync(FULL, free_head, 0);
-        tree_len = __shfl_sync(FULL, tree_len, 0);
       }
     }
     if (overflow) {  // workspace too small: hand the read to the next lane
