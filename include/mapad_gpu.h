@@ -272,22 +272,40 @@ int mapad_gpu_gather_peak(int device, uint64_t table_bytes, uint32_t bytes_per_a
                           double* gbps_out);
 
 /* ---------------------------------------------------------------------------------------------
- * Callers and data formats either side of the hot path: FASTQ(.GZ) in, BAM out.
+ * Callers and data formats either side of the hot path: FASTQ(.GZ) / BAM in, BAM out.
  * ------------------------------------------------------------------------------------------- */
-/* FASTQ / FASTQ.GZ reader with the Record normalisation of src/map/record.rs:184-215 and the chunking and
- * bad-record skipping of src/map/input_chunk_reader.rs:176-244. */
+/* Input reader.  The format (FASTQ, FASTQ.GZ, BAM) is sniffed from the decompressed first bytes as in
+ * src/map/input_chunk_reader.rs:42-172 (CRAM: MAPAD_EINVAL).  Record normalisation of src/map/record.rs:138-215:
+ * FASTQ is upper-cased, Phred+33 removed, flags 0; BAM reads stored reverse-complemented (flag 16) are turned back,
+ * flags and auxiliary fields are kept.  Chunking and bad-record skipping of input_chunk_reader.rs:176-244. */
+int mapad_input_open(const char* path, void** reader_out);
+int mapad_input_is_bam(void* reader);
+const char* mapad_input_header_text(void* reader); /* SAM header text of a BAM input, NULL otherwise */
+int mapad_input_next_chunk(void* reader, uint64_t max_reads, void** chunk_out);
+void mapad_input_close(void* reader);
+/* older names of the same three calls */
 int mapad_fastq_open(const char* path, void** reader_out);
 int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out);
 void mapad_fastq_close(void* reader);
 uint64_t mapad_chunk_view(void* chunk, mapad_reads* reads, const char** names, const uint64_t** name_offsets,
                           const uint16_t** flags, uint64_t* skipped);
+/* raw BAM auxiliary fields of the chunk's reads: read i owns aux[aux_offsets[i] .. aux_offsets[i+1]) */
+int mapad_chunk_aux(void* chunk, const uint8_t** aux, const uint64_t** aux_offsets);
 void mapad_chunk_free(void* chunk);
-/* BAM writer: create_bam_header (src/map/mapping.rs:300-398) and create_bam_record (:722-927) from the per-read
- * fields of a mapad_results; records are written in input order (mapping.rs:291-293). */
+/* BAM writer: create_bam_header (src/map/mapping.rs:300-398; `src_header_text` = header of a BAM input, its @PG
+ * chain, @RG and @CO lines are carried over) and create_bam_record (:722-927; `aux` = the input's auxiliary fields,
+ * copied except for the tag filter of :829-846) from the per-read fields of a mapad_results; records are written in
+ * input order (mapping.rs:291-293). */
 int mapad_bam_open(const char* path, const mapad_index* index, const char* command_line, const char* read_group_id,
                    int force_overwrite, void** writer_out);
+int mapad_bam_open_with_header(const char* path, const mapad_index* index, const char* command_line,
+                               const char* read_group_id, int force_overwrite, const char* src_header_text,
+                               void** writer_out);
 int mapad_bam_write_chunk(void* writer, const mapad_index* index, const mapad_reads* reads, const char* names,
                           const uint64_t* name_offsets, const uint16_t* in_flags, const mapad_results* res);
+int mapad_bam_write_chunk_aux(void* writer, const mapad_index* index, const mapad_reads* reads, const char* names,
+                              const uint64_t* name_offsets, const uint16_t* in_flags, const uint8_t* aux,
+                              const uint64_t* aux_offsets, const mapad_results* res);
 int mapad_bam_close(void* writer);
 
 /* Test hook: evaluates the device restatements of the glibc float functions the reference reaches through

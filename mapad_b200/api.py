@@ -64,6 +64,14 @@ def lib():
             "mapad_gpu_destroy": (None, [vp]),
             "mapad_gpu_gather_peak": (i32, [i32, u64, u32, u64, P(C.c_double)]),
             "mapad_gpu_debug_libm": (i32, [i32, i32, i32, u64, vp, vp]),
+            "mapad_input_open": (i32, [C.c_char_p, P(vp)]),
+            "mapad_input_is_bam": (i32, [vp]),
+            "mapad_input_header_text": (C.c_char_p, [vp]),
+            "mapad_input_next_chunk": (i32, [vp, u64, P(vp)]),
+            "mapad_input_close": (None, [vp]),
+            "mapad_chunk_aux": (i32, [vp, P(vp), P(vp)]),
+            "mapad_bam_open_with_header": (i32, [C.c_char_p, vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, P(vp)]),
+            "mapad_bam_write_chunk_aux": (i32, [vp, vp, P(abi.Reads), vp, vp, vp, vp, vp, P(abi.Results)]),
             "mapad_fastq_open": (i32, [C.c_char_p, P(vp)]),
             "mapad_fastq_next_chunk": (i32, [vp, u64, P(vp)]),
             "mapad_fastq_close": (None, [vp]),
@@ -88,7 +96,8 @@ EXPORTED_SYMBOLS = [
     "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
     "mapad_fastq_open", "mapad_fastq_next_chunk", "mapad_fastq_close", "mapad_chunk_view", "mapad_chunk_free", "mapad_bam_open",
-    "mapad_bam_write_chunk", "mapad_bam_close",
+    "mapad_bam_write_chunk", "mapad_bam_close", "mapad_input_open", "mapad_input_is_bam", "mapad_input_header_text", "mapad_input_next_chunk",
+    "mapad_input_close", "mapad_chunk_aux", "mapad_bam_open_with_header", "mapad_bam_write_chunk_aux",
 ]
 
 
@@ -319,49 +328,64 @@ def debug_libm(fn, values, iarg=0, device=0):
     return y
 
 
-class FastqChunks:
-    """Iterates a FASTQ / FASTQ.GZ file in chunks of `batch_size` reads (`--batch_size`, src/main.rs:225-232).
-    Yields (abi.Reads, names_ptr, name_offsets_ptr, flags_ptr, n_reads, chunk_handle); free with .free(handle)."""
+class ReadChunks:
+    """Iterates a FASTQ / FASTQ.GZ / BAM file (format sniffed) in chunks of `batch_size` reads (`--batch_size`,
+    src/main.rs:225-232).  Yields (abi.Reads, names_ptr, name_offsets_ptr, flags_ptr, n_reads, chunk_handle); free with
+    .free(handle).  `header_text` is the SAM header of a BAM input (None for FASTQ)."""
 
     def __init__(self, path, batch_size=250_000):
         self.r = C.c_void_p()
-        _check(lib().mapad_fastq_open(path.encode(), C.byref(self.r)))
+        _check(lib().mapad_input_open(os.fsencode(path), C.byref(self.r)))
         self.batch_size = batch_size
         self.skipped = 0
+        self.is_bam = bool(lib().mapad_input_is_bam(self.r))
+        t = lib().mapad_input_header_text(self.r)
+        self.header_text = t.decode(errors="replace") if t is not None else None
 
     def __iter__(self):
         return self
 
     def __next__(self):
-        ch = C.c_void_p()
-        _check(lib().mapad_fastq_next_chunk(self.r, self.batch_size, C.byref(ch)))
-        R = abi.Reads()
-        names, noff, flags, skipped = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
-        n = lib().mapad_chunk_view(ch, C.byref(R), C.byref(names), C.byref(noff), C.byref(flags), C.byref(skipped))
-        self.skipped += int(skipped.value)
-        if n == 0:
+        while True:
+            ch = C.c_void_p()
+            _check(lib().mapad_input_next_chunk(self.r, self.batch_size, C.byref(ch)))
+            R = abi.Reads()
+            names, noff, flags, skipped = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+            n = lib().mapad_chunk_view(ch, C.byref(R), C.byref(names), C.byref(noff), C.byref(flags), C.byref(skipped))
+            self.skipped += int(skipped.value)
+            if n:
+                return R, names, noff, flags, int(n), ch
             lib().mapad_chunk_free(ch)
-            raise StopIteration
-        return R, names, noff, flags, int(n), ch
+            if not skipped.value:  # a chunk of nothing but skipped records is not the end of the input
+                raise StopIteration
 
     def free(self, ch):
         lib().mapad_chunk_free(ch)
 
     def close(self):
         if self.r:
-            lib().mapad_fastq_close(self.r)
+            lib().mapad_input_close(self.r)
             self.r = None
 
 
+FastqChunks = ReadChunks
+
+
 class BamWriter:
-    def __init__(self, path, index, command_line="", read_group_id=None, force_overwrite=False):
+    def __init__(self, path, index, command_line="", read_group_id=None, force_overwrite=False, src_header_text=None):
         self.w = C.c_void_p()
         self.index = index
-        _check(lib().mapad_bam_open(path.encode(), index.h, command_line.encode(), read_group_id.encode() if read_group_id else None,
-                                    int(force_overwrite), C.byref(self.w)))
+        _check(lib().mapad_bam_open_with_header(os.fsencode(path), index.h, command_line.encode(),
+                                                read_group_id.encode() if read_group_id else None, int(force_overwrite),
+                                                src_header_text.encode() if src_header_text else None, C.byref(self.w)))
 
-    def write_chunk(self, reads_struct, names, name_offsets, flags, results_struct):
-        _check(lib().mapad_bam_write_chunk(self.w, self.index.h, C.byref(reads_struct), names, name_offsets, flags, C.byref(results_struct)))
+    def write_chunk(self, reads_struct, names, name_offsets, flags, results_struct, chunk=None):
+        """chunk: the ReadChunks handle the reads came from — its BAM auxiliary fields are carried over."""
+        aux, aoff = C.c_void_p(), C.c_void_p()
+        if chunk is not None:
+            _check(lib().mapad_chunk_aux(chunk, C.byref(aux), C.byref(aoff)))
+        _check(lib().mapad_bam_write_chunk_aux(self.w, self.index.h, C.byref(reads_struct), names, name_offsets, flags, aux, aoff,
+                                               C.byref(results_struct)))
 
     def close(self):
         if self.w:

@@ -6,8 +6,9 @@
     python -m mapad_b200.cli index -g genome.fa [--seed 1234]      # writes genome.fa.{tbw,tle,toc,trt,tsa,tpi,tos}
 
 Flag names and defaults follow /root/reference/src/main.rs:96-300.  `map` loads the seven index files next to the
-FASTA when they exist (as the reference does) and otherwise indexes the FASTA in memory.  Differences in this round:
-BAM/CRAM input is not read, and the per-read XD:f timing tag is not written.  Several chunks are kept in flight (--inflight) so that the
+FASTA when they exist (as the reference does) and otherwise indexes the FASTA in memory.  Reads come from FASTQ,
+FASTQ.GZ or BAM (flags, auxiliary fields and the @PG/@RG/@CO header lines of a BAM input are carried over like in
+create_bam_header / create_bam_record).  Differences: CRAM is not read, and the per-read XD:f timing tag is not written.  Several chunks are kept in flight (--inflight) so that the
 straggler reads of one chunk overlap with the next; records are written in input order.
 """
 import argparse
@@ -105,8 +106,9 @@ def run_map(a, argv):
         index = build_index(a.reference, a.seed, None)
     first = api.Mapper(index, params, device=a.device)
     mappers = [first] + [first.clone() for _ in range(max(1, a.inflight) - 1)]
-    writer = api.BamWriter(a.output, index, command_line=" ".join(argv), read_group_id=a.read_group, force_overwrite=a.force_overwrite)
-    chunks = api.FastqChunks(a.reads, a.batch_size)
+    chunks = api.ReadChunks(a.reads, a.batch_size)
+    writer = api.BamWriter(a.output, index, command_line=" ".join(argv), read_group_id=a.read_group, force_overwrite=a.force_overwrite,
+                           src_header_text=chunks.header_text)
     rng = np.random.default_rng(a.seed)
     done = {}
     lock = threading.Condition()
@@ -125,7 +127,7 @@ def run_map(a, argv):
             with lock:
                 while done.get("next", 0) != k:
                     lock.wait()
-                writer.write_chunk(R, names, noff, flags, res)
+                writer.write_chunk(R, names, noff, flags, res, chunk=ch)
                 recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
                 done["mapped"] = done.get("mapped", 0) + int(recs["mapped"].sum())
                 done["reads"] = done.get("reads", 0) + n

@@ -38,8 +38,49 @@ def read_bam(path):
                 tags[tag], = struct.unpack_from("<f", data, q); q += 4
             elif ty == "A":
                 tags[tag] = chr(data[q]); q += 1
+            elif ty in "cCsSI":
+                fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "I": "<I"}[ty]
+                tags[tag], = struct.unpack_from(fmt, data, q); q += struct.calcsize(fmt)
+            elif ty == "H":
+                e = data.index(b"\x00", q); tags[tag] = ("H", data[q:e].decode()); q = e + 1
+            elif ty == "B":
+                sub = chr(data[q]); cnt, = struct.unpack_from("<I", data, q + 1); q += 5
+                fmt = "<%d%s" % (cnt, {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i", "I": "I", "f": "f"}[sub])
+                tags[tag] = (sub, list(struct.unpack_from(fmt, data, q))); q += struct.calcsize(fmt)
             else:
                 raise ValueError(ty)
-        recs.append(dict(name=name, flag=flag, ref_id=ref_id, pos=pos, mapq=mapq, cigar=cigar, seq=seq, qual=qual, tags=tags))
+        tag_order = list(tags)
+        recs.append(dict(tag_order=tag_order, name=name, flag=flag, ref_id=ref_id, pos=pos, mapq=mapq, cigar=cigar, seq=seq, qual=qual, tags=tags))
         p = end
     return text, refs, recs
+
+
+def bgzf_block(payload):
+    """One BGZF block (SAM spec 4.1): gzip member with the BC extra field."""
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = co.compress(payload) + co.flush()
+    bsize = len(body) + 25
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + body +
+            struct.pack("<II", zlib.crc32(payload) & 0xFFFFFFFF, len(payload)))
+
+
+def write_bam(path, header_text, refs, records, block=40_000):
+    """records: dicts with name, flag, seq, qual (bytes of raw Phred or None), aux (raw bytes); all unplaced."""
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(header_text)) + header_text.encode() + struct.pack("<i", len(refs)))
+    for name, ln in refs:
+        out += struct.pack("<i", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<i", ln)
+    for r in records:
+        name = r["name"].encode() + b"\x00"
+        seq = r["seq"]
+        codes = ["=ACMGRSVTWYHKDBN".index(c) for c in seq]
+        if len(codes) % 2:
+            codes.append(0)
+        packed = bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(codes), 2))
+        qual = r["qual"] if r["qual"] is not None else b"\xff" * len(seq)
+        body = struct.pack("<iiBBHHHiiii", -1, -1, len(name), 0, 4680, 0, r["flag"], len(seq), -1, -1, 0) + name + packed + qual + r.get("aux", b"")
+        out += struct.pack("<i", len(body)) + body
+    with open(path, "wb") as f:
+        for o in range(0, len(out), block):
+            f.write(bgzf_block(bytes(out[o:o + block])))
+        f.write(bgzf_block(b""))

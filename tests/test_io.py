@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from bamio import read_bam
+from bamio import read_bam, write_bam
 from emu import emu
 from helpers import product_params, revcomp
 from mapad_b200 import abi, api
@@ -107,3 +107,95 @@ def test_bam_flags(tmp_path):
     for rec in recs:
         assert rec["flag"] == exp[rec["name"]]["flags"], rec["name"]
         assert rec["tags"]["RG"] == "RG01"
+
+
+def test_bam_input_to_bam_output(tmp_path):
+    """BAM in -> BAM out (record.rs:138-182, create_bam_header, create_bam_record): the integration reads as the
+    reference's own BAM fixture stores them (flag-16 reads reverse-complemented, flags such as 589), with auxiliary
+    fields and a header to carry over."""
+    import struct
+    data = json.load(open(os.path.join(GOLDEN, "ref_integration.json")))
+    index = api.Index.build([(n, s) for n, s in data["contigs"]], draws="A")
+    aux = (b"XYZkeep me\x00" + b"NMi" + struct.pack("<i", 99) + b"RGZold\x00" + b"abBs" + struct.pack("<Ihhh", 3, 1, -2, 3) +
+           b"xff" + struct.pack("<f", 1.5) + b"ASC\x07" + b"xhH1AE301\x00" + b"XAZstale\x00" + b"zcc\xfe")
+    recs_in = [dict(name=r["name"], flag=r["flag"], seq=r["seq"], qual=bytes(c - 33 for c in r["qual"].encode()), aux=aux if i % 2 == 0 else b"")
+               for i, r in enumerate(data["reads"])]
+    recs_in.insert(3, dict(name="noqual", flag=4, seq="ACGTACGTAC", qual=None))  # missing qualities: skipped
+    header = ("@HD\tVN:1.0\tSO:queryname\n@SQ\tSN:stale\tLN:5\n@RG\tID:old\tSM:x\n@PG\tID:bwa\tPN:bwa\n"
+              "@PG\tID:mapAD\tPN:mapAD\tPP:bwa\n@CO\tfirst comment\n")
+    src = tmp_path / "in.bam"
+    write_bam(str(src), header, [("stale", 5)], recs_in, block=700)  # records straddle BGZF blocks
+    params = product_params(INTEGRATION_PARAMS)
+    exp = {e["name"]: e for e in data["expectation"]}
+
+    def run(read_group):
+        chunks = api.ReadChunks(str(src), batch_size=7)
+        assert chunks.is_bam and chunks.header_text == header.rstrip("\n") + "\n"
+        out = tmp_path / ("out_%s.bam" % (read_group or "none"))
+        w = api.BamWriter(str(out), index, command_line="mapad map bam", read_group_id=read_group, src_header_text=chunks.header_text)
+        total = 0
+        for R, names, noff, flags, n, ch in chunks:
+            tb = int(C.cast(R.offsets, C.POINTER(C.c_uint64))[n])
+            seq = np.ctypeslib.as_array(C.cast(R.seq, C.POINTER(C.c_uint8)), shape=(tb,)).copy()
+            qual = np.ctypeslib.as_array(C.cast(R.qual, C.POINTER(C.c_uint8)), shape=(tb,)).copy()
+            off = np.ctypeslib.as_array(C.cast(R.offsets, C.POINTER(C.c_uint64)), shape=(n + 1,)).copy()
+            res = emu.map_batch(index, params, seeds=np.arange(n, dtype=np.uint32) + 100, packed=(seq, qual, off))
+            rs, keep = abi.results_struct(res)
+            w.write_chunk(R, names, noff, flags, rs, chunk=ch)
+            total += n
+            chunks.free(ch)
+        w.close()
+        chunks.close()
+        assert total == 17 and chunks.skipped == 1
+        return read_bam(str(out))
+
+    text, refs, recs = run(None)
+    lines = text.rstrip("\n").split("\n")
+    assert lines[0] == "@HD\tVN:1.6\tSO:unsorted" and lines[1:5] == ["@SQ\tSN:chr1\tLN:600", "@SQ\tSN:Chromosome_02\tLN:600",
+                                                                    "@SQ\tSN:Chromosome_03\tLN:84", "@SQ\tSN:Chromosome_04\tLN:46"]
+    assert "stale" not in text
+    assert lines[5] == "@RG\tID:old\tSM:x" and lines[6] == "@PG\tID:bwa\tPN:bwa" and lines[7] == "@PG\tID:mapAD\tPN:mapAD\tPP:bwa"
+    assert lines[8].startswith("@PG\tID:mapAD.1\tPN:mapAD\t") and lines[8].endswith("\tCL:mapad map bam\tPP:mapAD")
+    assert lines[9] == "@CO\tfirst comment" and len(lines) == 10
+    assert [r["name"] for r in recs] == [r["name"] for r in data["reads"]]
+    for i, rec in enumerate(recs):
+        e = exp[rec["name"]]
+        assert rec["flag"] == e["flags"], rec["name"]  # e.g. 589 -> 577 (mapping.rs:748-776)
+        t = rec["tags"]
+        if i % 2 == 0:  # carried over, in input order, ahead of the new tags; filtered: NM AS XA of the input
+            assert rec["tag_order"][:6] == ["XY", "RG", "ab", "xf", "xh", "zc"], rec["tag_order"]
+            assert (t["XY"], t["RG"], t["ab"], t["xf"], t["xh"], t["zc"]) == ("keep me", "old", ("s", [1, -2, 3]), 1.5, ("H", "1AE301"), -2)
+        else:
+            assert "XY" not in t and "RG" not in t
+        if e["tid"] is None:
+            assert rec["flag"] & 4 and rec["ref_id"] == -1 and "NM" not in t and "AS" not in t and "XA" not in t
+            continue
+        assert (rec["ref_id"], rec["pos"] + 1, rec["mapq"], rec["cigar"], rec["seq"]) == (e["tid"], e["pos"], e["mq"], e["cigar"], e["seq"]), rec["name"]
+        assert (t["MD"], t["X0"], t["X1"], t["XT"], t.get("XA")) == (e["md"], e["x0"], e["x1"], e["xt"], e["xa"]), rec["name"]
+        assert t["NM"] != 99 and isinstance(t["AS"], float)
+
+    text, refs, recs = run("NEW")
+    assert "@RG\tID:NEW\n" in text and "ID:old" not in text
+    for i, rec in enumerate(recs):
+        assert rec["tags"]["RG"] == "NEW" and rec["tag_order"].count("RG") == 1
+        if i % 2 == 0:
+            assert rec["tag_order"][:6] == ["XY", "ab", "xf", "xh", "zc", "RG"]
+
+
+def test_input_sniffing(tmp_path):
+    plain = tmp_path / "r.fq"
+    plain.write_text("@r1 desc\nacgtn\n+\nIIII!\n@r2\nGG\n+\n#$\n")
+    ch = api.ReadChunks(str(plain), batch_size=10)
+    assert not ch.is_bam and ch.header_text is None
+    R, names, noff, flags, n, h = next(ch)
+    assert n == 2 and bytes(C.cast(R.seq, C.POINTER(C.c_uint8))[0:7]) == b"ACGTNGG"
+    assert list(C.cast(R.qual, C.POINTER(C.c_uint8))[0:7]) == [40, 40, 40, 40, 0, 2, 3]
+    ch.free(h)
+    ch.close()
+    cram = tmp_path / "x.cram"
+    cram.write_bytes(b"CRAM\x03\x00" + b"\x00" * 30)
+    try:
+        api.ReadChunks(str(cram))
+        assert False, "CRAM must be refused"
+    except api.MapadError as e:
+        assert e.code == -1
