@@ -239,6 +239,23 @@ def test_cli_fastq_to_bam(api, tmp_path):
                (s["tid"], s["pos"], s["mapq"], s["cigar"], s["md"], s["nm"]), i
         assert bool(rec["flag"] & 16) == bool(s["strand"])
         assert np.float32(rec["tags"]["AS"]) == np.float32(s["AS"])
+    # the same reads as an unaligned BAM (the usual aDNA input): identical records, input tags carried over
+    from bamio import write_bam
+    src = tmp_path / "r.bam"
+    write_bam(str(src), "@HD\tVN:1.6\n@PG\tID:leeHom\tPN:leeHom\n",
+              [], [dict(name="read%d" % i, flag=4, seq=s_.decode(), qual=bytes(q_), aux=b"XYZorig\x00") for i, (s_, q_) in enumerate(zip(seqs, quals))])
+    out2 = tmp_path / "o2.bam"
+    cmd2 = [c if c != str(fq) else str(src) for c in cmd]
+    cmd2[cmd2.index(str(out))] = str(out2)
+    r = subprocess.run(cmd2, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    text2, refs2, recs2 = read_bam(str(out2))
+    assert refs2 == refs and "@PG\tID:leeHom\tPN:leeHom\n" in text2 and "\tPP:leeHom\n" in text2
+    assert len(recs2) == len(recs)
+    for a, b in zip(recs, recs2):
+        assert b["tags"].pop("XY") == "orig"
+        b["tag_order"].remove("XY")
+        assert a == b, a["name"]
 
 
 def test_full_size_cfg1_properties(api):
