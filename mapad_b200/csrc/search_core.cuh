@@ -260,6 +260,15 @@ MAPAD_DEV void node_load(const NodeT<WIDE>& src, uint32_t id, Frame& f) {
   f.node = id;
 }
 
+// Optional per-step statistics for the host-side SIMT model (tools/simt_model.cpp); compiled out everywhere else.
+#if defined(MAPAD_STEP_STATS) && !defined(__CUDA_ARCH__)
+struct StepStats { int trickle, n_cand, pushes, bubble[9]; };
+extern thread_local StepStats* g_step_stats;
+#define MAPAD_STAT(x) do { if (g_step_stats) { x; } } while (0)
+#else
+#define MAPAD_STAT(x) do { } while (0)
+#endif
+
 // ---- min_max_heap::MinMaxHeap ------------------------------------------
 // Generic over the backing store H (get(i) / set(i, e)): a plain array for the per-thread version,
 // shared memory with a global-memory spill for the warp-cooperative kernel.
@@ -309,6 +318,7 @@ MAPAD_DEV void mm_push(const H& d, uint32_t& n, HeapEnt e) {
     climb_max = !min_level;
   }
   while (i >= 3) {
+    MAPAD_STAT(g_step_stats->bubble[g_step_stats->pushes > 0 ? g_step_stats->pushes - 1 : 0] += 1);
     uint32_t gp = (((i - 1) >> 1) - 1) >> 1;
     HeapEnt ge = d.get(gp);
     if (climb_max ? (e.score > ge.score) : (e.score < ge.score)) { d.set(i, ge); i = gp; } else break;
@@ -321,6 +331,7 @@ MAPAD_DEV void mm_trickle_down(const H& d, uint32_t n, uint32_t i) {
   while (true) {
     const uint32_t c1 = 2 * i + 1;
     if (c1 >= n) break;
+    MAPAD_STAT(g_step_stats->trickle += 1);
     const uint32_t g1 = 4 * i + 3;
     // the six candidates (2 children, 4 grandchildren) are fetched independently of each other so that a
     // level living in HBM costs one memory latency; candidate indices are increasing, so "stop at the first
@@ -472,6 +483,7 @@ MAPAD_DEV void check_and_push(WS& ws, SearchState<WIDE>& st, Frame f, uint32_t p
     return;
   }
   if (!ws.ensure_heap(st.heap_n)) { st.overflow = true; return; }
+  MAPAD_STAT(if (g_step_stats->pushes < 9) g_step_stats->pushes += 1);
   mm_push(ws.heap(), st.heap_n, HeapEnt{f.score, id});
 }
 
@@ -603,6 +615,7 @@ MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJo
       n_cand += 1;
     }
   }
+  MAPAD_STAT(g_step_stats->n_cand = n_cand);
   for (int i = 0; i < n_cand && !st.overflow; ++i) check_and_push<WIDE, WS>(ws, st, cand[i], sf.node, cand_op[i], L, bc, P);
   if (st.overflow) return STEP_OVERFLOW;
   if (st.heap_n > ctr.max_stack) ctr.max_stack = st.heap_n;
