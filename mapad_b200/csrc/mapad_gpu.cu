@@ -453,6 +453,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     // ---- throughput lane: one read per THREAD, workspaces grown in 64 KiB chunks from a pool that spans the whole
     //      workspace budget; reads that outgrow `max_nodes` restart in the warp-cooperative lanes below ----
     {
+      const uint32_t profile_iters = getenv("MAPAD_PROFILE_ITERS") ? (uint32_t)strtoul(getenv("MAPAD_PROFILE_ITERS"), nullptr, 0) : 0u;
       uint64_t pool_threads_env = 8192, max_nodes = 131072;
       if (const char* e = getenv("MAPAD_POOL_THREADS")) pool_threads_env = strtoull(e, nullptr, 10);
       if (const char* e = getenv("MAPAD_POOL_MAX_NODES")) max_nodes = strtoull(e, nullptr, 10);
@@ -496,11 +497,12 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
         k_search_pool<WIDE><<<(unsigned)(pool_threads / tblock), tblock, 0, h->stream>>>(
             ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, pool, h->d_pool_tables.p, h->d_pool_hits.p, (uint32_t)stage_cap, work, n_work,
             deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p, (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
-            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu), trace_stats ? h->d_lane_stats.p : nullptr);
+            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu), trace_stats ? h->d_lane_stats.p : nullptr, profile_iters);
         ++launches;
         CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
+        if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the thread lane was cut short for profiling, no results"; return MAPAD_ELIMIT; }
         const uint32_t n_def = h->h_cur.p->n_deferred;
         trace("pool", n_work, n_def, stage_cap);
         if (trace_stats) {

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128, MAPAD_POOL_MIN_BLOCKS)
 k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ bound_table, const PenRow* __restrict__ delta,
               const float* __restrict__ dcomp, ChunkPool pool, uint32_t* tables, HitTmp* hit_base, uint32_t max_nodes,
               const uint32_t* __restrict__ work_list, uint32_t n_work, uint32_t* deferred_list, Cursors* cur, ReadMid* mid,
-              mapad_hit* hit_pool, uint32_t hit_cap, mapad_edit_op* op_pool, uint32_t op_cap, unsigned long long* lane_stats) {
+              mapad_hit* hit_pool, uint32_t hit_cap, mapad_edit_op* op_pool, uint32_t op_cap, unsigned long long* lane_stats, uint32_t iter_budget) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t busy_iters = 0;
   PoolWorkspace<WIDE> ws;
@@ -170,6 +170,9 @@ k_search_pool(DevIndex ix, DevParams P, ReadBatch rb, const float* __restrict__ 
     }
     const int rc = search_step<WIDE>(ix, P, job, ws, st, ctr);
     busy_iters += 1;
+    // profiling aid (MAPAD_PROFILE_ITERS): stop after a fixed number of expansions per thread so that a launch consists of
+    // the saturated phase only and is short enough for ncu's replays; the host discards the batch (MAPAD_ELIMIT)
+    if (iter_budget && busy_iters >= iter_budget) break;
     if (rc == STEP_CONTINUE) continue;
     have = false;
     if (rc == STEP_OVERFLOW) {  // outgrew this lane (or the pool ran dry): hand the read to the warp-cooperative lanes
