@@ -491,6 +491,9 @@ MAPAD_DEV void check_and_push(WS& ws, SearchState<WIDE>& st, Frame f, uint32_t p
 //   begin; while (step == STEP_CONTINUE);
 // as a FLAT loop in which a thread that finishes a read picks up its next one, so that the 32 reads of a warp
 // stay in the same loop body instead of waiting for the slowest read of a round.
+#ifndef MAPAD_COMPACT_CAND
+#define MAPAD_COMPACT_CAND 0
+#endif
 enum { STEP_CONTINUE = 0, STEP_DONE = 1, STEP_OVERFLOW = 2 };
 struct SearchJob {
   const uint8_t* seq;
@@ -556,6 +559,68 @@ MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJo
   // (insertion; then for T,G,C,A: deletion, match/mismatch), and then replayed through ONE copy of
   // check_and_push in a run-time loop: with 32 independent reads per warp this keeps the threads in the same
   // instructions instead of nine separately predicated copies of the push code.
+#if MAPAD_COMPACT_CAND
+  // Variant (round-2 candidate, off by default): the nine candidates are kept as 4-bit codes (type, base index) in one
+  // register and rebuilt from the popped frame in the push loop, instead of nine 56-byte frames in local memory — the
+  // per-thread stack of k_search_pool (760 B x 512 threads per SM) is larger than L1 and competes with the heaps.
+  uint64_t codes = 0;
+  int n_cand = 0;
+  {  // insertion (mapping.rs:1213-1242)
+    int dist = j < L - j - 1 ? j : L - j - 1;
+    if (!bound_reject(bc, fadd(insertion_score, lower_bound)) && dist >= P.gap_dist_ends) { codes |= 0ull << (4 * n_cand); n_cand += 1; }
+  }
+  BiIv ext[4];
+  {
+    BiIv in = forward ? BiIv{sf.iv.lower_rev, sf.iv.lower, sf.iv.size} : sf.iv;
+    extend_all<WIDE>(ix, in, ext);
+  }
+  const bool del_ok = !bound_reject(bc, fadd(deletion_score, lower_bound));
+  const int dist5 = forward ? j : j + 1;
+  const int dist3 = L - dist5;
+  const bool del_dist_ok = (dist5 < dist3 ? dist5 : dist3) >= P.gap_dist_ends;
+  const uint8_t read_base = job.seq[j];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (ext[k].size < 1) continue;
+    const int pen_idx = forward ? k : 3 - k;  // rank = 4 - k; forward: 4 - rank, backward: rank - 1
+    if (del_ok && del_dist_ok) { codes |= (uint64_t)(4 | k) << (4 * n_cand); n_cand += 1; }
+    const float mm_score = fadd(row.d[pen_idx], sf.score);
+    if (!bound_reject(bc, fadd(mm_score, lower_bound))) { codes |= (uint64_t)(8 | k) << (4 * n_cand); n_cand += 1; }
+  }
+  MAPAD_STAT(g_step_stats->n_cand = n_cand);
+  for (int i = 0; i < n_cand && !st.overflow; ++i) {
+    const uint32_t code = (uint32_t)(codes >> (4 * i)) & 15u;
+    const uint32_t type = code >> 2, k = code & 3u;
+    Frame ch = sf;
+    uint32_t op;
+    if (type == 0) {
+      ch.start = child_start; ch.len = sf.len + 1;
+      if (forward) ch.gap_f = GAP_INS; else ch.gap_b = GAP_INS;
+      ch.score = insertion_score; ch.ngaps = num_gaps_open;
+      op = pack_op(j, MAPAD_ED_INSERTION, 0);
+    } else {
+      BiIv ip = k == 0 ? ext[0] : (k == 1 ? ext[1] : (k == 2 ? ext[2] : ext[3]));
+      const int rank = 4 - (int)k;
+      uint8_t c;
+      if (forward) { ip = BiIv{ip.lower_rev, ip.lower, ip.size}; c = complement_base(rank_base(rank)); }
+      else c = rank_base(rank);
+      ch.iv = ip;
+      if (type == 1) {
+        if (forward) ch.gap_f = GAP_DEL; else ch.gap_b = GAP_DEL;
+        ch.score = deletion_score; ch.ngaps = num_gaps_open;
+        op = pack_op(j, MAPAD_ED_DELETION, c);
+      } else {
+        const int pen_idx = forward ? (int)k : 3 - (int)k;
+        const float pen = pen_idx == 0 ? row.d[0] : (pen_idx == 1 ? row.d[1] : (pen_idx == 2 ? row.d[2] : row.d[3]));
+        ch.start = child_start; ch.len = sf.len + 1;
+        if (forward) ch.gap_f = GAP_CLOSED; else ch.gap_b = GAP_CLOSED;
+        ch.score = fadd(pen, sf.score);
+        op = c == read_base ? pack_op(j, MAPAD_ED_MATCH, 0) : pack_op(j, MAPAD_ED_MISMATCH, c);
+      }
+    }
+    check_and_push<WIDE, WS>(ws, st, ch, sf.node, op, L, bc, P);
+  }
+#else
   Frame cand[9];
   uint32_t cand_op[9];
   int n_cand = 0;
@@ -617,6 +682,7 @@ MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJo
   }
   MAPAD_STAT(g_step_stats->n_cand = n_cand);
   for (int i = 0; i < n_cand && !st.overflow; ++i) check_and_push<WIDE, WS>(ws, st, cand[i], sf.node, cand_op[i], L, bc, P);
+#endif
   if (st.overflow) return STEP_OVERFLOW;
   if (st.heap_n > ctr.max_stack) ctr.max_stack = st.heap_n;
   // early exits (mapping.rs:1348-1355)

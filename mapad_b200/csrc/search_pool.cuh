@@ -54,6 +54,12 @@ __global__ void k_pool_init(ChunkPool p, uint32_t first_free) {
 
 #define MAPAD_POOL_MAX_NODE_CHUNKS 64
 #define MAPAD_POOL_MAX_HEAP_CHUNKS 16
+// Variant (round-2 candidate, off by default): heap entry i lives in slot i + 1.  With the 1-based numbering the two
+// children of a node share one aligned 16-byte block and its four grandchildren exactly one 32-byte sector, so a
+// trickle-down level reads 2 sectors instead of 3.5 on average (0-based: grandchildren start at byte 32 i + 24).
+#ifndef MAPAD_HEAP_SHIFT
+#define MAPAD_HEAP_SHIFT 0
+#endif
 
 template <bool WIDE>
 struct PoolWorkspace {
@@ -76,6 +82,7 @@ struct PoolWorkspace {
                                            (size_t)(id & ((1u << NPC_SHIFT) - 1u)) * sizeof(NodeT<WIDE>));
   }
   __device__ __forceinline__ HeapEnt* heap_slot(uint32_t i) const {
+    i += MAPAD_HEAP_SHIFT;
     if (i < (1u << HPC_SHIFT)) return heap0 + i;
     const uint32_t c = table[MAPAD_POOL_MAX_NODE_CHUNKS + (i >> HPC_SHIFT)];
     return reinterpret_cast<HeapEnt*>(pool.base + (size_t)c * MAPAD_CHUNK_BYTES) + (i & ((1u << HPC_SHIFT) - 1u));
@@ -92,7 +99,7 @@ struct PoolWorkspace {
     return true;
   }
   __device__ __forceinline__ bool ensure_heap(uint32_t n) {
-    const uint32_t c = n >> HPC_SHIFT;
+    const uint32_t c = (n + MAPAD_HEAP_SHIFT) >> HPC_SHIFT;
     if (c < n_heap_chunks) return true;
     if (c >= MAPAD_POOL_MAX_HEAP_CHUNKS) return false;
     const uint32_t got = pool_acquire(pool);

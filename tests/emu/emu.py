@@ -10,7 +10,9 @@ from mapad_b200 import abi, api
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
-_LIB = os.path.join(_HERE, "libmapad_emu.so")
+# MAPAD_EMU_DEFS="-DMAPAD_COMPACT_CAND=1 ...": build and load a variant of the device logic (its own .so)
+_DEFS = os.environ.get("MAPAD_EMU_DEFS", "").split()
+_LIB = os.path.join(_HERE, "libmapad_emu%s.so" % ("_" + "_".join(d.replace("-D", "").replace("=", "") for d in _DEFS) if _DEFS else ""))
 _lib = None
 
 
@@ -19,7 +21,7 @@ def build(force=False):
     srcs = [os.path.join(_HERE, "emu_harness.cpp")] + [os.path.join(csrc, f) for f in ("host_index.cpp", "host_params.cpp", "dev_index_build.cpp")]
     deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc)]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(d) > os.path.getmtime(_LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-o", _LIB] + srcs)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-o", _LIB] + _DEFS + srcs)
     return _LIB
 
 

@@ -145,3 +145,18 @@ def test_continuous_bound_and_custom_model():
     want = ora.map_batch(oix, oracle_params(spec2), seqs, quals, seeds=seeds, n_threads=4, want_hits=True)
     got = emu.map_batch(index, P, seqs, quals, seeds=seeds)
     compare_results(want, got)
+
+
+def test_device_logic_variants():
+    """Build-time variants of the device logic that are candidates for the next tuning round must stay bit-exact too:
+    the whole emulation suite is re-run against each variant build (MAPAD_EMU_DEFS)."""
+    import subprocess
+    import sys
+    if os.environ.get("MAPAD_EMU_DEFS"):
+        pytest.skip("already inside a variant run")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for defs in ("-DMAPAD_COMPACT_CAND=1",):
+        env = dict(os.environ, MAPAD_EMU_DEFS=defs)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emulated_kernels.py"), "-x", "-q", "-k", "not variants"],
+                           env=env, cwd=os.path.dirname(here), capture_output=True, text=True, timeout=1500)
+        assert r.returncode == 0, defs + "\n" + r.stdout[-3000:] + r.stderr[-2000:]
