@@ -9,9 +9,11 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mapad_gpu.h"
@@ -65,46 +67,75 @@ struct FastqReader {  // despite the name: the sniffing reader for FASTQ, FASTQ.
 // ---------------------------------------------------------------------------------------------------------------
 // BGZF / BAM
 // ---------------------------------------------------------------------------------------------------------------
+// One BGZF block (SAM spec 4.1) from up to 0xff00 input bytes; `out` must hold 65536 + 1024 bytes.  Returns its size, 0 on error.
+size_t bgzf_compress(const uint8_t* data, size_t n, uint8_t* out, int level) {
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return 0;
+  zs.next_in = const_cast<uint8_t*>(data);
+  zs.avail_in = (uInt)n;
+  zs.next_out = out + 18;
+  zs.avail_out = 65536 + 1024 - 18 - 8;
+  const int rc = deflate(&zs, Z_FINISH);
+  const size_t clen = zs.total_out;
+  deflateEnd(&zs);
+  if (rc != Z_STREAM_END) return 0;
+  const size_t bsize = clen + 18 + 8;
+  if (bsize > 65536) return 0;
+  static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+  memcpy(out, hdr, 16);
+  out[16] = (uint8_t)((bsize - 1) & 0xff); out[17] = (uint8_t)((bsize - 1) >> 8);
+  const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data, (uInt)n);
+  const uint32_t isize = (uint32_t)n;
+  memcpy(out + 18 + clen, &crc, 4);
+  memcpy(out + 18 + clen + 4, &isize, 4);
+  return bsize;
+}
+
 struct BamWriter {
+  static constexpr size_t BLOCK = 0xff00;
   FILE* f = nullptr;
-  std::vector<uint8_t> pending;
+  std::vector<uint8_t> pending;  // uncompressed bytes not yet written (less than one block between calls)
   std::vector<std::string> contig_names;
   std::string read_group;  // ID or empty
-  bool flush_block(const uint8_t* data, size_t n) {
-    uint8_t out[65536 + 1024];
-    z_stream zs;
-    memset(&zs, 0, sizeof zs);
-    if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-    zs.next_in = const_cast<uint8_t*>(data);
-    zs.avail_in = (uInt)n;
-    zs.next_out = out + 18;
-    zs.avail_out = sizeof out - 18 - 8;
-    int rc = deflate(&zs, Z_FINISH);
-    if (rc != Z_STREAM_END) { deflateEnd(&zs); return false; }
-    const size_t clen = zs.total_out;
-    deflateEnd(&zs);
-    const size_t bsize = clen + 18 + 8;
-    static const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-    memcpy(out, hdr, 16);
-    out[16] = (uint8_t)((bsize - 1) & 0xff); out[17] = (uint8_t)((bsize - 1) >> 8);
-    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), data, (uInt)n);
-    const uint32_t isize = (uint32_t)n;
-    memcpy(out + 18 + clen, &crc, 4);
-    memcpy(out + 18 + clen + 4, &isize, 4);
-    return fwrite(out, 1, bsize, f) == bsize;
+  int level = 6;
+  unsigned n_threads = 1;
+  // Compresses all full blocks of `pending` (BGZF blocks are independent: one worker per slice of blocks) and writes them
+  // in order; with `all` also the trailing partial block.
+  bool flush(bool all) {
+    const size_t n_blocks = all ? (pending.size() + BLOCK - 1) / BLOCK : pending.size() / BLOCK;
+    if (n_blocks == 0) return true;
+    const size_t stride = 65536 + 1024;
+    std::vector<uint8_t> out(n_blocks * stride);
+    std::vector<size_t> out_len(n_blocks, 0);
+    auto work = [&](size_t b0, size_t b1) {
+      for (size_t b = b0; b < b1; ++b) {
+        const size_t o = b * BLOCK, n = std::min(BLOCK, pending.size() - o);
+        out_len[b] = bgzf_compress(pending.data() + o, n, out.data() + b * stride, level);
+      }
+    };
+    const size_t nt = std::min<size_t>(n_threads, n_blocks);
+    if (nt <= 1) {
+      work(0, n_blocks);
+    } else {
+      std::vector<std::thread> th;
+      for (size_t t = 0; t < nt; ++t) th.emplace_back(work, n_blocks * t / nt, n_blocks * (t + 1) / nt);
+      for (std::thread& t : th) t.join();
+    }
+    for (size_t b = 0; b < n_blocks; ++b) {
+      if (!out_len[b] || fwrite(out.data() + b * stride, 1, out_len[b], f) != out_len[b]) return false;
+    }
+    const size_t consumed = std::min(pending.size(), n_blocks * BLOCK);
+    pending.erase(pending.begin(), pending.begin() + consumed);
+    return true;
   }
   bool write(const void* p, size_t n) {
     const uint8_t* b = (const uint8_t*)p;
     pending.insert(pending.end(), b, b + n);
-    while (pending.size() >= 0xff00) {
-      if (!flush_block(pending.data(), 0xff00)) return false;
-      pending.erase(pending.begin(), pending.begin() + 0xff00);
-    }
     return true;
   }
   bool finish() {
-    if (!pending.empty() && !flush_block(pending.data(), pending.size())) return false;
-    pending.clear();
+    if (!flush(true)) return false;
     static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     return fwrite(eof, 1, 28, f) == 28;
   }
@@ -377,6 +408,12 @@ int mapad_bam_open_with_header(const char* path, const mapad_index* index, const
   if (!w->f) { delete w; return MAPAD_EIO; }
   w->contig_names = ix->contig_names;
   if (read_group_id) w->read_group = read_group_id;
+  {  // BGZF blocks are compressed by a few host threads (MAPAD_BAM_THREADS, default min(hardware threads, 16))
+    const char* e = getenv("MAPAD_BAM_THREADS");
+    unsigned hw = std::thread::hardware_concurrency();
+    w->n_threads = e ? (unsigned)std::max(1, atoi(e)) : std::max(1u, std::min(hw ? hw : 1u, 16u));
+    if (const char* l = getenv("MAPAD_BAM_LEVEL")) w->level = std::min(9, std::max(0, atoi(l)));
+  }
   // pick @RG / @PG / @CO lines out of the input header
   std::vector<std::string> src_rg, src_pg, src_co;
   if (src_header_text) {
@@ -439,7 +476,7 @@ int mapad_bam_open_with_header(const char* path, const mapad_index* index, const
     h.push_back(0);
     put32(h, (uint32_t)(ix->contig_end[i] - ix->contig_start[i] + 1));
   }
-  if (!w->write(h.data(), h.size())) { fclose(w->f); delete w; return MAPAD_EIO; }
+  if (!w->write(h.data(), h.size()) || !w->flush(false)) { fclose(w->f); delete w; return MAPAD_EIO; }
   *out = w;
   return MAPAD_OK;
 }
@@ -524,7 +561,7 @@ int mapad_bam_write_chunk_aux(void* writer, const mapad_index* index, const mapa
     memcpy(rec.data(), &bs, 4);
     if (!w->write(rec.data(), rec.size())) return MAPAD_EIO;
   }
-  return MAPAD_OK;
+  return w->flush(false) ? MAPAD_OK : MAPAD_EIO;
 }
 
 int mapad_bam_write_chunk(void* writer, const mapad_index* index, const mapad_reads* reads, const char* names, const uint64_t* name_offsets,

@@ -199,3 +199,30 @@ def test_input_sniffing(tmp_path):
         assert False, "CRAM must be refused"
     except api.MapadError as e:
         assert e.code == -1
+
+
+def test_bam_writer_threads_are_deterministic(tmp_path, monkeypatch):
+    """BGZF blocks are compressed by several host threads; the file must not depend on how many."""
+    data = json.load(open(os.path.join(GOLDEN, "ref_integration.json")))
+    index = api.Index.build([(n, s) for n, s in data["contigs"]], draws="A")
+    seqs = [r["seq"].encode() for r in data["reads"]] * 400  # ~6 800 records: several BGZF blocks
+    quals = [bytes(c - 33 for c in r["qual"].encode()) for r in data["reads"]] * 400
+    packed = abi.pack_reads(seqs, quals)
+    res = emu.map_batch(index, product_params(INTEGRATION_PARAMS), seeds=np.arange(len(seqs), dtype=np.uint32), packed=packed)
+    rs, keep = abi.results_struct(res)
+    R, keep2 = api.make_reads(*packed)
+    names = b"".join(b"r%06d" % i for i in range(len(seqs)))
+    noff = (np.arange(len(seqs) + 1, dtype=np.uint64) * 7)
+    fl = np.zeros(len(seqs), dtype=np.uint16)
+    blobs = []
+    for nt in ("1", "5"):
+        monkeypatch.setenv("MAPAD_BAM_THREADS", nt)
+        out = tmp_path / ("t%s.bam" % nt)
+        w = api.BamWriter(str(out), index, force_overwrite=True)
+        for _ in range(3):
+            w.write_chunk(R, C.c_char_p(names), noff.ctypes.data, fl.ctypes.data, rs)
+        w.close()
+        blobs.append(open(out, "rb").read())
+    assert blobs[0] == blobs[1] and len(blobs[0]) > 200_000
+    text, refs, recs = read_bam(str(tmp_path / "t5.bam"))
+    assert len(recs) == 3 * len(seqs) and recs[-1]["name"] == "r%06d" % (len(seqs) - 1)
