@@ -214,6 +214,15 @@ struct HitTmp {  // HitInterval before its edit operations are extracted
 #define MAPAD_MAX_HITS 20   // the search returns once len() > 9, one expansion adds at most 9 (mapping.rs:1348)
 #define MAPAD_NO_NODE 0xffffffffu
 
+// Optional per-step statistics for the host-side SIMT model (tools/simt_model.cpp); compiled out everywhere else.
+#if defined(MAPAD_STEP_STATS) && !defined(__CUDA_ARCH__)
+struct StepStats { int trickle, n_cand, pushes, bubble[9]; int n_heap_idx; uint32_t heap_idx[512]; };
+extern thread_local StepStats* g_step_stats;
+#define MAPAD_STAT(x) do { if (g_step_stats) { x; } } while (0)
+#else
+#define MAPAD_STAT(x) do { } while (0)
+#endif
+
 // Workspace policies.  A workspace provides: node(id) -> NodeT&, ensure_node(id) / ensure_heap(n) (grow or
 // refuse), heap() -> a store with get/set, and the hit array.  `Workspace` is the contiguous per-thread /
 // per-warp arena; PoolWorkspace (search_pool.cuh) grows in fixed-size chunks taken from a shared pool.
@@ -234,8 +243,8 @@ struct Workspace {  // one per persistent thread; lives in global memory
   MAPAD_DEV uint32_t min_cap() const { return cap; }
   struct Store {
     HeapEnt* d;
-    MAPAD_DEV HeapEnt get(uint32_t i) const { return d[i]; }
-    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { d[i] = e; }
+    MAPAD_DEV HeapEnt get(uint32_t i) const { MAPAD_STAT(if (g_step_stats->n_heap_idx < 512) g_step_stats->heap_idx[g_step_stats->n_heap_idx++] = i); return d[i]; }
+    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { MAPAD_STAT(if (g_step_stats->n_heap_idx < 512) g_step_stats->heap_idx[g_step_stats->n_heap_idx++] = i); d[i] = e; }
   };
   MAPAD_DEV Store heap() const { return Store{heap_}; }
 };
@@ -259,15 +268,6 @@ MAPAD_DEV void node_load(const NodeT<WIDE>& src, uint32_t id, Frame& f) {
   f.gap_f = n.gap_f; f.gap_b = n.gap_b; f.ngaps = n.ngaps;
   f.node = id;
 }
-
-// Optional per-step statistics for the host-side SIMT model (tools/simt_model.cpp); compiled out everywhere else.
-#if defined(MAPAD_STEP_STATS) && !defined(__CUDA_ARCH__)
-struct StepStats { int trickle, n_cand, pushes, bubble[9]; };
-extern thread_local StepStats* g_step_stats;
-#define MAPAD_STAT(x) do { if (g_step_stats) { x; } } while (0)
-#else
-#define MAPAD_STAT(x) do { } while (0)
-#endif
 
 // ---- min_max_heap::MinMaxHeap ------------------------------------------
 // Generic over the backing store H (get(i) / set(i, e)): a plain array for the per-thread version,

@@ -20,6 +20,44 @@
 namespace mapad { thread_local StepStats* g_step_stats = nullptr; }
 using namespace mapad;
 
+// physical slot (in 8-byte entries) of heap index i under the three candidate layouts
+static inline uint64_t slot_linear0(uint32_t i) { return i; }
+static inline uint64_t slot_linear1(uint32_t i) { return (uint64_t)i + 1; }
+// "family" layout: levels 0,1 in line 0; for k >= 1 the two children (level 2k) and four grandchildren (level 2k+1) of
+// every node of level 2k-1 share one 64-byte line (6 of 8 slots used) — what one pop_max trickle-down step reads
+static inline uint64_t slot_family(uint32_t i) {
+  const uint32_t y = i + 1;
+  const int lvl = 31 - __builtin_clz(y);
+  if (lvl < 2) return i;
+  const int odd = lvl & 1;
+  const uint32_t o1 = y >> (1 + odd);
+  const int lo = lvl - 1 - odd;
+  const uint32_t j = o1 ^ (1u << lo);
+  const uint32_t a = 0xAAAAAAAAu & ((1u << (lo - 1)) - 1u);
+  const uint64_t line = 1ull + a + j;
+  const uint32_t sl = odd ? 2u + (y & 3u) : (y & 1u);
+  return line * 8 + sl;
+}
+template <class F>
+static void count_lines(const StepStats& st, F slot, uint32_t hot_below, double& sectors, double& lines) {
+  // distinct 32-byte sectors / 64-byte lines among the heap entries one expansion touched, ignoring the top of the heap
+  // (indices < hot_below are assumed to stay cached)
+  uint64_t sec[512], lin[512];
+  int ns = 0, nl = 0;
+  for (int k = 0; k < st.n_heap_idx; ++k) {
+    if (st.heap_idx[k] < hot_below) continue;
+    const uint64_t b = slot(st.heap_idx[k]) * 8;
+    const uint64_t s_ = b >> 5, l_ = b >> 6;
+    bool f = false;
+    for (int q = 0; q < ns; ++q) if (sec[q] == s_) { f = true; break; }
+    if (!f) sec[ns++] = s_;
+    f = false;
+    for (int q = 0; q < nl; ++q) if (lin[q] == l_) { f = true; break; }
+    if (!f) lin[nl++] = l_;
+  }
+  sectors += ns; lines += nl;
+}
+
 struct Lane {
   std::vector<HeapEnt> heap;
   std::vector<NodeT<false>> nodes;
@@ -31,7 +69,7 @@ struct Lane {
   bool have = false;
 };
 
-extern "C" int simt_model(const mapad_index* index, const mapad_params* params, const mapad_reads* in, uint32_t cap, double* out8) {
+extern "C" int simt_model(const mapad_index* index, const mapad_params* params, const mapad_reads* in, uint32_t cap, double* out8, double* heap6) {
   const HostIndex* hix = reinterpret_cast<const HostIndex*>(index);
   IndexMeta meta;
   std::vector<uint8_t> blob;
@@ -83,7 +121,7 @@ extern "C" int simt_model(const mapad_index* index, const mapad_params* params, 
     bool any = false;
     for (int l = 0; l < 32; ++l) {
       Lane& ln = lanes[l];
-      memset(&ss[l], 0, sizeof ss[l]);
+      ss[l].trickle = ss[l].pushes = ss[l].n_heap_idx = 0; memset(ss[l].bubble, 0, sizeof ss[l].bubble);
       ss[l].n_cand = -1;  // idle lane
       while (!ln.have && next < in->n_reads) {
         const uint64_t r = next++;
@@ -102,6 +140,12 @@ extern "C" int simt_model(const mapad_index* index, const mapad_params* params, 
       const int src = search_step<false>(ix, P, ln.job, ln.ws, ln.st, ln.ctr);
       g_step_stats = nullptr;
       frames += 1;
+      if (heap6) {
+        count_lines(ss[l], slot_linear0, 31, heap6[0], heap6[1]);
+        count_lines(ss[l], slot_linear1, 31, heap6[2], heap6[3]);
+        count_lines(ss[l], slot_family, 31, heap6[4], heap6[5]);
+        heap6[6] += ss[l].n_heap_idx;
+      }
       if (src != STEP_CONTINUE) { ln.have = false; if (src == STEP_OVERFLOW) skipped += 1; }
     }
     if (!any) break;
