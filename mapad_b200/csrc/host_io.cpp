@@ -35,7 +35,7 @@ struct ReadChunk {
   uint64_t skipped = 0;
 };
 
-struct FastqReader {  // despite the name: the sniffing reader for FASTQ, FASTQ.GZ and BAM
+struct InputReader {  // the sniffing reader for FASTQ, FASTQ.GZ and BAM
   gzFile f = nullptr;  // gzopen reads plain files transparently, and BGZF is a series of gzip members
   bool is_bam = false;
   std::string header_text;  // BAM input: the SAM header text
@@ -226,7 +226,7 @@ extern "C" {
 int mapad_input_open(const char* path, void** out) {
   if (!path || !out) return MAPAD_EINVAL;
   *out = nullptr;
-  FastqReader* r = new (std::nothrow) FastqReader();
+  InputReader* r = new (std::nothrow) InputReader();
   if (!r) return MAPAD_ENOMEM;
   r->f = gzopen(path, "rb");
   if (!r->f) { delete r; return MAPAD_EIO; }
@@ -257,15 +257,15 @@ int mapad_input_open(const char* path, void** out) {
   return MAPAD_OK;
 }
 int mapad_fastq_open(const char* path, void** out) { return mapad_input_open(path, out); }
-int mapad_input_is_bam(void* reader) { return reader && ((FastqReader*)reader)->is_bam ? 1 : 0; }
+int mapad_input_is_bam(void* reader) { return reader && ((InputReader*)reader)->is_bam ? 1 : 0; }
 // SAM header text of a BAM input (NULL for FASTQ); valid until the reader is closed.
 const char* mapad_input_header_text(void* reader) {
-  FastqReader* r = (FastqReader*)reader;
+  InputReader* r = (InputReader*)reader;
   return r && r->is_bam ? r->header_text.c_str() : nullptr;
 }
 
 // BAM records -> Record (record.rs:138-182).
-static int bam_next_chunk(FastqReader* r, uint64_t max_reads, ReadChunk* c) {
+static int bam_next_chunk(InputReader* r, uint64_t max_reads, ReadChunk* c) {
   std::vector<uint8_t> blk;
   while ((uint64_t)c->flags.size() < max_reads) {
     uint32_t block_size;
@@ -323,7 +323,7 @@ static int bam_next_chunk(FastqReader* r, uint64_t max_reads, ReadChunk* c) {
 // sequence and quality lengths differ or that are longer than i16::MAX are skipped like there (:200-214, record.rs:188).
 int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) {
   if (!reader || !chunk_out) return MAPAD_EINVAL;
-  FastqReader* r = (FastqReader*)reader;
+  InputReader* r = (InputReader*)reader;
   ReadChunk* c = new (std::nothrow) ReadChunk();
   if (!c) return MAPAD_ENOMEM;
   if (r->is_bam) {
@@ -360,7 +360,7 @@ int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) {
 }
 int mapad_input_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) { return mapad_fastq_next_chunk(reader, max_reads, chunk_out); }
 void mapad_fastq_close(void* reader) {
-  FastqReader* r = (FastqReader*)reader;
+  InputReader* r = (InputReader*)reader;
   if (r) { if (r->f) gzclose(r->f); delete r; }
 }
 void mapad_input_close(void* reader) { mapad_fastq_close(reader); }
