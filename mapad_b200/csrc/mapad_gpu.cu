@@ -494,7 +494,11 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
         ++launches;
         CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));
         if (trace_stats) { CK(h->d_lane_stats.reserve(2)); CK(cudaMemsetAsync(h->d_lane_stats.p, 0, 16, h->stream)); }
-        k_search_pool<WIDE><<<(unsigned)(pool_threads / tblock), tblock, 0, h->stream>>>(
+        // tuning aid: MAPAD_POOL_SMEM_PAD=<bytes> of unused dynamic shared memory per block limits how many blocks share an
+        // SM (e.g. 110000 -> 2, 74000 -> 3) without touching the kernel; 0 = the register-limited 4 blocks per SM
+        static const size_t smem_pad = getenv("MAPAD_POOL_SMEM_PAD") ? (size_t)strtoull(getenv("MAPAD_POOL_SMEM_PAD"), nullptr, 10) : 0;
+        if (smem_pad) CK(cudaFuncSetAttribute(k_search_pool<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pad));
+        k_search_pool<WIDE><<<(unsigned)(pool_threads / tblock), tblock, smem_pad, h->stream>>>(
             ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, pool, h->d_pool_tables.p, h->d_pool_hits.p, (uint32_t)stage_cap, work, n_work,
             deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p, (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
             (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu), trace_stats ? h->d_lane_stats.p : nullptr, profile_iters);
