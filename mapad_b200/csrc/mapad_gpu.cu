@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -22,6 +23,7 @@
 #include "../../include/mapad_gpu.h"
 #include "dev_index_build.hpp"
 #include "epilogue_core.cuh"
+#include "search_group.cuh"
 #include "search_pool.cuh"
 #include "search_warp.cuh"
 #include "host_index.hpp"
@@ -194,6 +196,8 @@ struct mapad_gpu {
   DevBuf<Cursors> d_cur;
   DevBuf<uint8_t> d_ws;  // workspace pool shared by all lanes
   DevBuf<uint32_t> d_pool_next, d_pool_tables;
+  DevBuf<uint32_t> d_order;          // read ids, longest first (work list of the group kernel)
+  PinBuf<uint32_t> h_order;
   DevBuf<HitTmp> d_pool_hits;
   DevBuf<unsigned long long> d_lane_stats;
   DevBuf<mapad_hit> d_hits;
@@ -339,7 +343,7 @@ void mapad_gpu_destroy(mapad_gpu* h) {
   h->d_seq.release(); h->d_qual.release(); h->d_offsets.release(); h->d_seeds.release(); h->d_starts.release();
   h->d_custom.release(); h->d_bound.release(); h->d_qualtab.release(); h->d_dpen.release(); h->d_dcomp.release();
   h->d_delta.release(); h->d_dsteps.release(); h->d_deferred_a.release(); h->d_deferred_b.release(); h->d_mid.release();
-  h->d_cur.release(); h->d_ws.release(); h->d_pool_next.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_lane_stats.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
+  h->d_cur.release(); h->d_ws.release(); h->d_pool_next.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_lane_stats.release(); h->d_order.release(); h->h_order.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
   h->d_records.release();
   h->h_seq.release(); h->h_qual.release(); h->h_offsets.release(); h->h_seeds.release(); h->h_records.release();
   h->h_hits.release(); h->h_ops.release(); h->h_cigar.release(); h->h_text.release(); h->h_cur.release();
@@ -364,6 +368,15 @@ static int upload_batch(mapad_gpu* h, const mapad_reads* in) {
   CK(cudaMemcpyAsync(h->d_seq.p, h->h_seq.p, tb, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_qual.p, h->h_qual.p, tb, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_offsets.p, h->h_offsets.p, (n + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  {  // work list of the search kernel: longest reads first (counting sort by length; work per read grows steeply with it)
+    CK(h->h_order.reserve(n + 1)); CK(h->d_order.reserve(n + 1));
+    const uint32_t max_len = h->prep.max_len;
+    std::vector<uint32_t> cnt((size_t)max_len + 2, 0);
+    for (uint64_t r = 0; r < n; ++r) cnt[max_len - (uint32_t)(in->offsets[r + 1] - in->offsets[r]) + 1] += 1;
+    for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+    for (uint64_t r = 0; r < n; ++r) h->h_order.p[cnt[max_len - (uint32_t)(in->offsets[r + 1] - in->offsets[r])]++] = (uint32_t)r;
+    CK(cudaMemcpyAsync(h->d_order.p, h->h_order.p, n * 4, cudaMemcpyHostToDevice, h->stream));
+  }
   h->has_seeds = in->seeds != nullptr;
   if (h->has_seeds) {
     CK(h->h_seeds.reserve(n + 1)); CK(h->d_seeds.reserve(n + 1));
@@ -385,6 +398,116 @@ static int upload_batch(mapad_gpu* h, const mapad_reads* in) {
   CK(cudaMemcpyAsync(h->d_qualtab.p, h->prep.qual_table, 256 * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));  // prep.* host vectors may be reused afterwards
   h->have_batch = true;
+  return MAPAD_OK;
+}
+
+
+// ---- K2 driver: the group kernel (search_group.cuh) ---------------------------------------------
+// One launch maps every read of the batch; a read is only handed back (deferred) when the chunk pool runs dry, and
+// then re-run with fewer groups in flight, i.e. more pool per group.
+struct GroupShape { int g, topl; };
+static GroupShape group_shape() {
+  static const GroupShape shape = [] {
+    GroupShape s{8, 11};
+    if (const char* e = getenv("MAPAD_GROUP")) s.g = atoi(e);
+    if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 32) s.g = 8;
+    s.topl = s.g == 1 ? 3 : (s.g == 32 ? 43 : 11);
+    if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43) s.topl = t; }
+    return s;
+  }();
+  return shape;
+}
+
+template <bool WIDE, int G, int TOPL>
+static cudaError_t launch_group_kernel(const GroupLaunch<WIDE>& a, uint32_t n_groups, cudaStream_t stream) {
+  constexpr int gpb = MAPAD_GROUP_BLOCK / G;
+  const size_t smem = (size_t)gpb * TOPL * 64;
+  cudaError_t e = cudaFuncSetAttribute(k_search_group<WIDE, G, TOPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_search_group<WIDE, G, TOPL><<<n_groups / gpb, MAPAD_GROUP_BLOCK, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+template <bool WIDE>
+static cudaError_t launch_group_dispatch(const GroupShape& sh, const GroupLaunch<WIDE>& a, uint32_t n_groups, cudaStream_t stream) {
+#define MAPAD_GROUP_CASE(G_, T_) if (sh.g == G_ && sh.topl == T_) return launch_group_kernel<WIDE, G_, T_>(a, n_groups, stream)
+  MAPAD_GROUP_CASE(1, 3); MAPAD_GROUP_CASE(1, 11);
+  MAPAD_GROUP_CASE(4, 11);
+  MAPAD_GROUP_CASE(8, 11); MAPAD_GROUP_CASE(8, 43);
+  MAPAD_GROUP_CASE(32, 43);
+#undef MAPAD_GROUP_CASE
+  return launch_group_kernel<WIDE, 8, 11>(a, n_groups, stream);
+}
+
+template <bool WIDE>
+static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams& P, const ReadBatch& rb, uint64_t& launches,
+                              const std::function<void(const char*, uint64_t, uint64_t, uint64_t)>& trace) {
+  const uint64_t n = h->n_reads;
+  GroupShape sh = group_shape();
+  if (sh.topl == 3 && sh.g != 1) sh.topl = 11;
+  const uint32_t gpb = (uint32_t)(MAPAD_GROUP_BLOCK / sh.g);
+  GroupLaunch<WIDE> a;
+  a.ix = ix; a.P = P; a.rb = rb;
+  a.bound_table = h->d_bound.p; a.delta = h->d_delta.p; a.dcomp = h->d_dcomp.p;
+  if ((uint64_t)P.edit_tree_limit + 64 > 0x7fffffffull || (uint64_t)P.stack_limit + 64 > 0x7fffffffull) {
+    h->err = "stack / edit-tree limits above 2^31 are not supported";
+    return MAPAD_EINVAL;
+  }
+  a.max_nodes = P.edit_tree_limit + 64u;
+  a.max_heap = P.stack_limit + 64u;
+  a.nt = (a.max_nodes >> (MAPAD_GCHUNK_SHIFT - 5u)) + 1u;
+  a.ht = (heap_lines_for(a.max_heap) >> (MAPAD_GCHUNK_SHIFT - 6u)) + 1u;
+  uint64_t n_chunks = h->ws_budget >> MAPAD_GCHUNK_SHIFT;
+  if (const char* e = getenv("MAPAD_TEST_POOL_CHUNKS")) n_chunks = std::min<uint64_t>(n_chunks, strtoull(e, nullptr, 10));  // test hook: tiny pool
+  // resident groups per SM: 16 warps of G = 8 lanes (64 reads); per-thread mode: 512 threads
+  uint64_t per_sm = sh.g == 1 ? 512 : (sh.g == 32 ? 16 : (uint64_t)(512 / sh.g));
+  if (const char* e = getenv("MAPAD_GROUPS_PER_SM")) per_sm = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+  uint64_t slots = per_sm * (uint64_t)h->n_sm;
+  if (const char* e = getenv("MAPAD_GROUPS")) slots = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+  slots = std::min<uint64_t>(slots, n_chunks / 4);  // two owned chunks per group, at least half of the pool for growth
+  const uint32_t profile_iters = getenv("MAPAD_PROFILE_ITERS") ? (uint32_t)strtoul(getenv("MAPAD_PROFILE_ITERS"), nullptr, 0) : 0u;
+  uint32_t n_work = (uint32_t)n;
+  const uint32_t* work = h->d_order.p;
+  uint32_t* deferred = h->d_deferred_a.p;
+  for (int attempt = 0; n_work > 0; ++attempt) {
+    uint64_t use = std::min<uint64_t>(slots, ((uint64_t)n_work + gpb - 1) / gpb * gpb);
+    use = use / gpb * gpb;
+    if (use < gpb) {
+      if (n_chunks < 2ull * gpb + 2) { h->err = "search workspace does not fit the device memory budget"; return MAPAD_ELIMIT; }
+      use = gpb;
+    }
+    CK(h->d_pool_next.reserve(n_chunks + 2));
+    CK(h->d_pool_tables.reserve(use * (size_t)(a.nt + a.ht)));
+    CK(h->d_pool_hits.reserve(use * MAPAD_MAX_HITS));
+    a.pool.base = h->d_ws.p;
+    a.pool.n_chunks = (uint32_t)n_chunks;
+    a.pool.next = h->d_pool_next.p + 2;
+    a.pool.head = reinterpret_cast<unsigned long long*>(h->d_pool_next.p);
+    a.tables = h->d_pool_tables.p;
+    a.hit_base = h->d_pool_hits.p;
+    a.work_list = work; a.n_work = n_work; a.deferred_list = deferred;
+    a.cur = h->d_cur.p; a.mid = h->d_mid.p;
+    a.hit_pool = h->d_hits.p; a.hit_cap = (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu);
+    a.op_pool = h->d_ops.p; a.op_cap = (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu);
+    a.iter_budget = profile_iters;
+    a.flags_or = attempt ? 2u : 0u;
+    k_gpool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(a.pool, (uint32_t)(2 * use));
+    ++launches;
+    CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter
+    CK(launch_group_dispatch<WIDE>(sh, a, (uint32_t)use, h->stream));
+    ++launches;
+    CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the search was cut short for profiling, no results"; return MAPAD_ELIMIT; }
+    const uint32_t n_def = h->h_cur.p->n_deferred;
+    trace("group", n_work, n_def, use);
+    if (n_def == 0) break;
+    if (use <= gpb && n_def >= n_work) { h->err = "reads exceeded the search workspace even with the smallest number of groups in flight"; return MAPAD_ELIMIT; }
+    work = deferred;
+    deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
+    n_work = n_def;
+    slots = std::max<uint64_t>(gpb, use / 8);
+  }
   return MAPAD_OK;
 }
 
@@ -440,6 +563,12 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
   for (int attempt = 0;; ++attempt) {
     CK(h->d_hits.reserve(hit_cap)); CK(h->d_ops.reserve(op_cap)); CK(h->d_cigar.reserve(cig_cap)); CK(h->d_text.reserve(text_cap));
     CK(cudaMemsetAsync(h->d_cur.p, 0, sizeof(Cursors), h->stream));
+    // ---- K2: search ----
+    static const bool legacy_search = getenv("MAPAD_SEARCH") && !strcmp(getenv("MAPAD_SEARCH"), "legacy");
+    if (!legacy_search) {
+      const int rc = search_with_groups<WIDE>(h, ix, P, rb, launches, trace);
+      if (rc) return rc;
+    } else {
     // ---- K2: search, lane by lane (warp per read; reads that outgrow a lane's workspace move to the next) ----
     const size_t per_entry = sizeof(HeapEnt) + sizeof(NodeT<WIDE>);
     const uint64_t full_cap = (uint64_t)std::max(P.stack_limit, P.edit_tree_limit) + 32;
@@ -566,9 +695,13 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
       n_work = n_def;
       cap *= 16;
     }
+    }
     CK(cudaEventRecord(h->ev[3], h->stream));
+    // K2 bump-allocates hits and edit operations; when a cursor overshot its pool the batch is re-run with larger pools
+    // BEFORE K3 would read the truncated spans (h_cur was copied after the last search launch)
+    const bool k2_over = n && (h->h_cur.p->hit_cursor > h->d_hits.cap || h->h_cur.p->op_cursor > h->d_ops.cap || (h->h_cur.p->overflow & 1u));
     // ---- K3: epilogue ----
-    if (n) {
+    if (n && !k2_over) {
       OutPools pools;
       pools.cigar = h->d_cigar.p; pools.cigar_cap = (uint32_t)std::min<size_t>(h->d_cigar.cap, 0xffffffffu);
       pools.cigar_cursor = &h->d_cur.p->cigar_cursor;
@@ -587,7 +720,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     CK(cudaGetLastError());
     trace("epilogue", n, 0, 0);
     const Cursors c = *h->h_cur.p;
-    const bool over = c.hit_cursor > h->d_hits.cap || c.op_cursor > h->d_ops.cap || c.cigar_cursor > h->d_cigar.cap ||
+    const bool over = k2_over || c.hit_cursor > h->d_hits.cap || c.op_cursor > h->d_ops.cap || c.cigar_cursor > h->d_cigar.cap ||
                       c.text_cursor > h->d_text.cap || (c.overflow & 1u) || c.pad;
     if (!over) break;
     if (attempt >= 3) { h->err = "output pools overflowed repeatedly"; return MAPAD_ELIMIT; }

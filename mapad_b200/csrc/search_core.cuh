@@ -251,21 +251,51 @@ struct Workspace {  // one per persistent thread; lives in global memory
 
 struct SearchCounters { uint32_t frames_popped, tree_nodes, max_stack, limit_hit; };
 
-template <bool WIDE>
-MAPAD_DEV void node_store(NodeT<WIDE>& dst, const Frame& f, uint32_t parent, uint32_t op) {
-  NodeT<WIDE> n;
+// 32-byte node of the wide layout (text < 2^40 symbols): the three interval fields carry 40 bits each, so that one
+// node is exactly one sector for both layouts (search_group.cuh).
+struct alignas(16) NodeW32 {
+  uint32_t parent, op;
+  uint32_t lower_lo, lower_rev_lo, size_lo;
+  uint8_t lower_hi, lower_rev_hi, size_hi, gaps;  // gaps = gap_f | gap_b << 2
+  int16_t start, len;
+  uint8_t ngaps, pad0;
+  uint16_t pad1;
+};
+
+template <class N>
+MAPAD_DEV void node_store(N& dst, const Frame& f, uint32_t parent, uint32_t op) {
+  N n;
   n.parent = parent; n.op = op;
   n.lower = (decltype(n.lower))f.iv.lower; n.lower_rev = (decltype(n.lower))f.iv.lower_rev; n.size = (decltype(n.lower))f.iv.size;
   n.start = (int16_t)f.start; n.len = (int16_t)f.len;
   n.gap_f = (uint8_t)f.gap_f; n.gap_b = (uint8_t)f.gap_b; n.ngaps = (uint8_t)f.ngaps; n.pad0 = 0; n.pad1 = 0;
   dst = n;
 }
-template <bool WIDE>
-MAPAD_DEV void node_load(const NodeT<WIDE>& src, uint32_t id, Frame& f) {
-  NodeT<WIDE> n = src;
+MAPAD_DEV void node_store(NodeW32& dst, const Frame& f, uint32_t parent, uint32_t op) {
+  NodeW32 n;
+  n.parent = parent; n.op = op;
+  n.lower_lo = (uint32_t)f.iv.lower; n.lower_rev_lo = (uint32_t)f.iv.lower_rev; n.size_lo = (uint32_t)f.iv.size;
+  n.lower_hi = (uint8_t)(f.iv.lower >> 32); n.lower_rev_hi = (uint8_t)(f.iv.lower_rev >> 32); n.size_hi = (uint8_t)(f.iv.size >> 32);
+  n.gaps = (uint8_t)(f.gap_f | (f.gap_b << 2));
+  n.start = (int16_t)f.start; n.len = (int16_t)f.len;
+  n.ngaps = (uint8_t)f.ngaps; n.pad0 = 0; n.pad1 = 0;
+  dst = n;
+}
+template <class N>
+MAPAD_DEV void node_load(const N& src, uint32_t id, Frame& f) {
+  N n = src;
   f.iv.lower = n.lower; f.iv.lower_rev = n.lower_rev; f.iv.size = n.size;
   f.start = n.start; f.len = n.len;
   f.gap_f = n.gap_f; f.gap_b = n.gap_b; f.ngaps = n.ngaps;
+  f.node = id;
+}
+MAPAD_DEV void node_load(const NodeW32& src, uint32_t id, Frame& f) {
+  NodeW32 n = src;
+  f.iv.lower = (uint64_t)n.lower_lo | ((uint64_t)n.lower_hi << 32);
+  f.iv.lower_rev = (uint64_t)n.lower_rev_lo | ((uint64_t)n.lower_rev_hi << 32);
+  f.iv.size = (uint64_t)n.size_lo | ((uint64_t)n.size_hi << 32);
+  f.start = n.start; f.len = n.len;
+  f.gap_f = n.gaps & 3; f.gap_b = n.gaps >> 2; f.ngaps = n.ngaps;
   f.node = id;
 }
 
@@ -475,7 +505,7 @@ MAPAD_DEV void check_and_push(WS& ws, SearchState<WIDE>& st, Frame f, uint32_t p
     st.node_hi += 1;
   }
   st.tree_len += 1;
-  node_store<WIDE>(ws.node(id), f, parent_node, op);
+  node_store(ws.node(id), f, parent_node, op);
   if (f.len == L) {
     HitTmp h;
     h.score = f.score; h.node = id; h.lower = f.iv.lower; h.lower_rev = f.iv.lower_rev; h.size = f.iv.size;
@@ -521,7 +551,7 @@ MAPAD_DEV int search_begin(const DevIndex& ix, const SearchJob& job, WS& ws, Sea
   root.iv = BiIv{0, 0, ix.m.n};
   root.start = job.start_pos; root.len = 0; root.gap_f = GAP_CLOSED; root.gap_b = GAP_CLOSED; root.ngaps = 0;
   root.score = 0.0f; root.node = 0;
-  node_store<WIDE>(ws.node(0), root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
+  node_store(ws.node(0), root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
   st.node_hi = 1; st.tree_len = 1;
   mm_push(ws.heap(), st.heap_n, HeapEnt{0.0f, 0});
   return STEP_CONTINUE;
@@ -536,7 +566,7 @@ MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJo
   if (!mm_pop_max(ws.heap(), st.heap_n, top)) { ctr.tree_nodes = st.tree_len; return STEP_DONE; }
   ctr.frames_popped += 1;
   Frame sf;
-  node_load<WIDE>(ws.node(top.node), top.node, sf);
+  node_load(ws.node(top.node), top.node, sf);
   sf.score = top.score;
   int j, d_k, d_l;
   bool forward;
@@ -727,7 +757,7 @@ MAPAD_DEV uint32_t path_length(const A& nodes, uint32_t node, int start_pos, uin
   uint32_t total = 0;
   n_left = 0;
   while (node != 0) {
-    const NodeT<WIDE>& nd = nodes.node(node);
+    const auto& nd = nodes.node(node);
     uint32_t op = nd.op;
     total += 1;
     if ((int)(op & 0xffffu) < start_pos) n_left += 1;
@@ -740,7 +770,7 @@ MAPAD_DEV void path_write(const A& nodes, uint32_t node, int start_pos, uint32_t
   uint32_t li = 0, ri = total;
   (void)n_left;
   while (node != 0) {
-    const NodeT<WIDE>& nd = nodes.node(node);
+    const auto& nd = nodes.node(node);
     uint32_t op = nd.op;
     mapad_edit_op e;
     e.pos = (uint16_t)(op & 0xffffu); e.kind = (uint8_t)((op >> 16) & 0xffu); e.base = (uint8_t)(op >> 24);

@@ -1,0 +1,617 @@
+// search_group.cuh — K2: the search kernel.  One read per lane GROUP (G consecutive lanes of a warp; G = 1 .. 32 is a
+// compile-time choice), persistent groups pulling reads from a global queue (longest reads first), and one flat loop in
+// which every iteration pops and expands ONE frame of the group's current read.  A read is never restarted: its state
+// grows in 256 KiB chunks taken from a pool in HBM until the reference's own limits (STACK_LIMIT / EDIT_TREE_LIMIT,
+// /root/reference/src/map/mapping.rs:52-54) are reached.
+//
+// Per-read state and where it lives:
+//   * min-max heap of (score, node) pairs — 64-byte FAMILY lines: the line owned by the node at 1-based position h of
+//     an odd (max) level holds the two children 2h, 2h+1 and the four grandchildren 4h .. 4h+3 of h, i.e. exactly the six
+//     entries one trickle-down step of MinMaxHeap::pop_max looks at.  The first TOPL lines (positions 1 .. 63 for
+//     TOPL = 11) sit in shared memory, the rest in pooled chunks.  The logical array — and therefore every tie — is
+//     that of min_max_heap::MinMaxHeap; only the physical placement differs.
+//   * edit tree = frame storage: one 32-byte node (one sector) per accepted child, both layouts (wide: 40-bit
+//     interval fields), bump-allocated, slab free list through `parent` (backtrack_tree.rs:34-53)
+//   * hits: std BinaryHeap emulation in a small per-group array
+// The sequential semantics are those of search_core.cuh::search_step (mapping.rs:932-1383): all lanes of a group run
+// the same decisions on the same data; the lanes share the memory work (see the cooperative sections below).
+#pragma once
+#include "search_core.cuh"
+#include "simt.cuh"
+
+namespace mapad {
+
+#ifndef MAPAD_GCHUNK_SHIFT
+#define MAPAD_GCHUNK_SHIFT 18u  // 256 KiB chunks; the emulation tests also build a 4 KiB variant to stress the chunk tables
+#endif
+#define MAPAD_GCHUNK_BYTES (1u << MAPAD_GCHUNK_SHIFT)
+#define MAPAD_GPOOL_EMPTY 0xffffffffu
+
+// Treiber stack of free chunk ids; the 32-bit tag in the upper half of `head` defeats ABA.
+struct GChunkPool {
+  uint8_t* base;
+  uint32_t n_chunks;
+  unsigned long long* head;
+  uint32_t* next;
+};
+
+MAPAD_DEV uint32_t gpool_acquire(const GChunkPool& p) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p.head);
+  while (true) {
+    const uint32_t idx = (uint32_t)old;
+    if (idx == MAPAD_GPOOL_EMPTY) return idx;
+    const uint32_t nxt = reinterpret_cast<volatile uint32_t*>(p.next)[idx];
+    const unsigned long long neu = (((old >> 32) + 1ull) << 32) | nxt;
+    const unsigned long long seen = atomicCAS(p.head, old, neu);
+    if (seen == old) return idx;
+    old = seen;
+  }
+#else
+  const uint32_t idx = (uint32_t)*p.head;
+  if (idx == MAPAD_GPOOL_EMPTY) return idx;
+  *p.head = p.next[idx];
+  return idx;
+#endif
+}
+MAPAD_DEV void gpool_release(const GChunkPool& p, uint32_t idx) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p.head);
+  while (true) {
+    reinterpret_cast<volatile uint32_t*>(p.next)[idx] = (uint32_t)old;
+    __threadfence();
+    const unsigned long long neu = (((old >> 32) + 1ull) << 32) | idx;
+    const unsigned long long seen = atomicCAS(p.head, old, neu);
+    if (seen == old) return;
+    old = seen;
+  }
+#else
+  p.next[idx] = (uint32_t)*p.head;
+  *p.head = idx;
+#endif
+}
+
+// ---- family layout of the min-max heap ----------------------------------------------------------
+// 1-based position x -> (line, slot).  Positions 1..3 live in line 0 (slots 0..2).  A position on an even level >= 2
+// is a CHILD of its owner x >> 1 (slots 0, 1), one on an odd level >= 3 a GRANDCHILD of its owner x >> 2 (slots 2..5).
+// Owners are the positions of odd levels; the owner o of level lo gets line  o - C(lo),  C(lo) = (2^(lo+1) - 1) / 3.
+struct HLoc { uint32_t line, slot; };
+MAPAD_DEV int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return __builtin_clz(x);
+#endif
+}
+MAPAD_DEV HLoc heap_loc(uint32_t x) {
+  if (x < 4u) return HLoc{0u, x - 1u};
+  const int lvl = 31 - clz32(x);
+  const uint32_t odd = (uint32_t)lvl & 1u;
+  const uint32_t owner = x >> (1u + odd);
+  const uint32_t slot = odd ? 2u + (x & 3u) : (x & 1u);
+  const int lo = lvl - 1 - (int)odd;
+  const uint32_t c = 0x55555555u & ((2u << lo) - 1u);
+  return HLoc{owner - c, slot};
+}
+// number of lines that positions 1..n occupy
+MAPAD_DEV uint32_t heap_lines_for(uint32_t n) {
+  if (n < 4u) return 1u;
+  const int lvl = 31 - clz32(n);
+  // the last position of the deepest even level <= lvl decides
+  const uint32_t x = (lvl & 1) ? ((1u << lvl) - 1u) : n;
+  return heap_loc(x).line + 1u;
+}
+
+struct alignas(16) ulonglong2_compat { unsigned long long a, b; };
+MAPAD_DEV float u32_as_f32(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { uint32_t u; float f; } c; c.u = u; return c.f;
+#endif
+}
+
+template <bool WIDE> struct GNodeOf { using type = NodeT<false>; };
+template <> struct GNodeOf<true> { using type = NodeW32; };
+
+// Workspace of one group (search_core.cuh's workspace concept).  Every lane of the group holds the same copy and makes
+// the same calls; pool operations are done once, by lane 0, and broadcast.
+template <bool WIDE, int G, int TOPL>
+struct GroupWorkspace {
+  using Node = typename GNodeOf<WIDE>::type;
+  static constexpr uint32_t NPC_SHIFT = MAPAD_GCHUNK_SHIFT - 5u;  // nodes per chunk (32 B each)
+  static constexpr uint32_t LPC_SHIFT = MAPAD_GCHUNK_SHIFT - 6u;  // heap lines per chunk (64 B each)
+  GChunkPool pool;
+  uint32_t* table;       // this group's chunk table: [0, nt) node chunks, [nt, nt + ht) heap chunks
+  uint32_t nt, ht;
+  uint32_t n_node_chunks, n_heap_chunks;
+  Node* node0;           // chunk 0 of each kind is owned for good: no table lookup for small searches
+  HeapEnt* heap0;
+  HeapEnt* top;          // shared memory: TOPL lines of 8 entries
+  HitTmp* hits;
+  uint32_t max_nodes, max_heap;
+  int gl;                // lane in group
+
+  MAPAD_DEV Node& node(uint32_t id) const {
+    if (id < (1u << NPC_SHIFT)) return node0[id];
+    const uint32_t c = table[id >> NPC_SHIFT];
+    return reinterpret_cast<Node*>(pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT))[id & ((1u << NPC_SHIFT) - 1u)];
+  }
+  MAPAD_DEV HeapEnt* line_ptr(uint32_t line) const {
+    if (line < (uint32_t)TOPL) return top + (line << 3);
+    const uint32_t g = line;  // the pooled storage is addressed by the plain line number (lines < TOPL unused there)
+    if (g < (1u << LPC_SHIFT)) return heap0 + ((size_t)g << 3);
+    const uint32_t c = table[nt + (g >> LPC_SHIFT)];
+    return reinterpret_cast<HeapEnt*>(pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT)) + ((size_t)(g & ((1u << LPC_SHIFT) - 1u)) << 3);
+  }
+  MAPAD_DEV HeapEnt* slot_ptr(uint32_t i0) const {  // 0-based logical index
+    const HLoc l = heap_loc(i0 + 1u);
+    return line_ptr(l.line) + l.slot;
+  }
+  MAPAD_DEV uint32_t acquire_chunk() const {
+    uint32_t got = MAPAD_GPOOL_EMPTY;
+    if (gl == 0) got = gpool_acquire(pool);
+    return Grp<G>::shfl(got, 0);
+  }
+  MAPAD_DEV bool ensure_node(uint32_t id) {
+    if (id >= max_nodes) return false;
+    const uint32_t c = id >> NPC_SHIFT;
+    if (c < n_node_chunks) return true;
+    if (c >= nt) return false;
+    const uint32_t got = acquire_chunk();
+    if (got == MAPAD_GPOOL_EMPTY) return false;
+    table[c] = got;
+    n_node_chunks = c + 1;
+    return true;
+  }
+  MAPAD_DEV bool ensure_heap(uint32_t n0) {  // room for logical index n0
+    if (n0 >= max_heap) return false;
+    const HLoc l = heap_loc(n0 + 1u);
+    if (l.line < (uint32_t)TOPL) return true;
+    const uint32_t c = l.line >> LPC_SHIFT;
+    if (c < n_heap_chunks) return true;
+    if (c >= ht) return false;
+    const uint32_t got = acquire_chunk();
+    if (got == MAPAD_GPOOL_EMPTY) return false;
+    table[nt + c] = got;
+    n_heap_chunks = c + 1;
+    return true;
+  }
+  MAPAD_DEV uint32_t min_cap() const { return max_nodes; }
+  MAPAD_DEV void release_extra() {  // keep chunk 0 of each kind
+    if (gl == 0) {
+      for (uint32_t c = n_node_chunks; c > 1; --c) gpool_release(pool, table[c - 1]);
+      for (uint32_t c = n_heap_chunks; c > 1; --c) gpool_release(pool, table[nt + c - 1]);
+    }
+    n_node_chunks = 1;
+    n_heap_chunks = 1;
+  }
+  struct Store {
+    const GroupWorkspace* w;
+    MAPAD_DEV HeapEnt get(uint32_t i) const { return *w->slot_ptr(i); }
+    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { *w->slot_ptr(i) = e; }
+  };
+  MAPAD_DEV Store heap() const { return Store{this}; }
+};
+
+// Everything one launch needs (passed by value as the kernel parameter).
+template <bool WIDE>
+struct GroupLaunch {
+  DevIndex ix;
+  DevParams P;
+  ReadBatch rb;
+  const float* bound_table;
+  const PenRow* delta;
+  const float* dcomp;
+  GChunkPool pool;
+  uint32_t* tables;        // n_groups x (nt + ht)
+  uint32_t nt, ht;
+  HitTmp* hit_base;        // n_groups x MAPAD_MAX_HITS
+  uint32_t max_nodes, max_heap;
+  const uint32_t* work_list;  // read ids in processing order (longest first), or nullptr
+  uint32_t n_work;
+  uint32_t* deferred_list;
+  Cursors* cur;
+  ReadMid* mid;
+  mapad_hit* hit_pool;
+  uint32_t hit_cap;
+  mapad_edit_op* op_pool;
+  uint32_t op_cap;
+  uint32_t iter_budget;    // profiling aid: stop every group after this many expansions (0 = off)
+  uint32_t flags_or;       // ORed into ReadMid::flags (bit 1: the read went through a retry launch)
+};
+
+// ---------------------------------------------------------------------------------------------
+// One read's search, executed by the G lanes of a group.  Memory discipline: the sequential state that lives in
+// registers (heap length, slab cursors, best hit) is computed identically by every lane; heap entries, tree nodes and
+// hits in memory are WRITTEN BY LANE 0 ONLY and read by all lanes, with a group barrier between a read phase and the
+// write phase that follows it (and between a write phase and the next read phase).  For G = 1 the barriers vanish and
+// this is a plain per-thread search.
+// ---------------------------------------------------------------------------------------------
+struct HeapLine6 { HeapEnt x[6]; };
+MAPAD_DEV HeapLine6 load_line6(const HeapEnt* ln) {  // three aligned 16-byte loads
+  HeapLine6 r;
+  const ulonglong2_compat* q = reinterpret_cast<const ulonglong2_compat*>(ln);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const ulonglong2_compat v = q[k];
+    r.x[2 * k].score = u32_as_f32((uint32_t)v.a); r.x[2 * k].node = (uint32_t)(v.a >> 32);
+    r.x[2 * k + 1].score = u32_as_f32((uint32_t)v.b); r.x[2 * k + 1].node = (uint32_t)(v.b >> 32);
+  }
+  return r;
+}
+
+template <bool WIDE, int G, int TOPL>
+struct GroupSearch {
+  using WS = GroupWorkspace<WIDE, G, TOPL>;
+  using Node = typename WS::Node;
+  WS ws;
+  uint32_t heap_n, node_hi, free_head, tree_len, n_hits;
+  float best_score;    // hits[0] of the BinaryHeap (its maximum) while n_hits > 0
+  uint64_t best_size;
+  uint32_t frames, limit_hit;
+  bool overflow;
+
+  MAPAD_DEV void wr(HeapEnt* p, HeapEnt e) const { if (ws.gl == 0) *p = e; }
+  MAPAD_DEV HeapEnt rd(uint32_t x1) const { const HLoc l = heap_loc(x1); return ws.line_ptr(l.line)[l.slot]; }
+  MAPAD_DEV HeapEnt* ptr(uint32_t x1) const { const HLoc l = heap_loc(x1); return ws.line_ptr(l.line) + l.slot; }
+
+  // MinMaxHeap::trickle_down_max from 1-based position h (2 or 3: the top of the max levels) with `e` in the hole;
+  // n = number of elements.  One family line per step.
+  MAPAD_DEV void trickle_max(uint32_t h, HeapEnt e, uint32_t n) {
+    HeapEnt* hpos = ws.top + (h - 1u);
+    uint32_t c_lo = 1u;  // C(level of h)
+    bool synced = false;
+    while (2u * h <= n) {
+      HeapEnt* ln = ws.line_ptr(h - c_lo);
+      const HeapLine6 f = load_line6(ln);
+      Grp<G>::sync();  // every lane holds the line (and everything read before) — lane 0 may write now
+      synced = true;
+      int best = -1;
+      float bk = e.score;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
+        if (idx <= n && f.x[c].score > bk) { best = c; bk = f.x[c].score; }
+      }
+      if (best < 0) break;
+      const HeapEnt be = f.x[best];
+      wr(hpos, be);
+      hpos = ln + best;
+      if (best < 2) break;  // moved to a child: done
+      const int pc = (best - 2) >> 1;  // the grandchild's parent is one of the two children in the same line
+      const HeapEnt pe = f.x[pc];
+      if (pe.score > e.score) { wr(ln + pc, e); e = pe; }
+      h = 4u * h + (uint32_t)(best - 2);
+      c_lo = (c_lo << 2) | 1u;
+    }
+    if (!synced) Grp<G>::sync();
+    wr(hpos, e);
+  }
+
+  // MinMaxHeap::push of `e` + Tree::add_node of `nd` at `id` (the two writes of an accepted child).
+  MAPAD_DEV void push(HeapEnt e, const Node& nd) {
+    const uint32_t x = heap_n + 1u;
+    heap_n = x;
+    Grp<G>::sync();  // writes of the previous phase are visible
+    HeapEnt pe = e;
+    bool moved = false;
+    uint32_t t = 0;
+    if (x > 1u) {
+      const uint32_t p = x >> 1;
+      pe = rd(p);
+      const bool min_level = ((31 - clz32(x)) & 1) == 0;
+      moved = min_level ? (e.score > pe.score) : (e.score < pe.score);
+      const bool climb_max = min_level == moved;
+      uint32_t c = moved ? p : x;
+      while (c >= 4u) {  // count the grandparent steps; nothing is written yet
+        const HeapEnt ae = rd(c >> 2);
+        if (climb_max ? (e.score > ae.score) : (e.score < ae.score)) { t += 1; c >>= 2; } else break;
+      }
+    }
+    Grp<G>::sync();  // every lane has finished reading
+    if (ws.gl == 0) {
+      ws.node(e.node) = nd;
+      uint32_t cur = x;
+      if (moved) { *ptr(x) = pe; cur = x >> 1; }
+      for (uint32_t k = 0; k < t; ++k) { *ptr(cur) = *ptr(cur >> 2); cur >>= 2; }
+      *ptr(cur) = e;
+    }
+  }
+
+  MAPAD_DEV void begin(const DevIndex& ix, int start_pos) {
+    heap_n = 0; node_hi = 1; free_head = MAPAD_NO_NODE; tree_len = 1; n_hits = 0; best_score = 0.0f; best_size = 0;
+    frames = 0; limit_hit = 0; overflow = false;
+    Frame root;
+    root.iv = BiIv{0, 0, ix.m.n};
+    root.start = start_pos; root.len = 0; root.gap_f = GAP_CLOSED; root.gap_b = GAP_CLOSED; root.ngaps = 0;
+    root.score = 0.0f; root.node = 0;
+    Node nd;
+    node_store(nd, root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
+    push(HeapEnt{0.0f, 0}, nd);
+    Grp<G>::sync();  // the root is visible to every lane before the first step reads it
+  }
+
+  // check_and_push_stack_frame (mapping.rs:932-987)
+  MAPAD_DEV void check_and_push(const Frame& f, uint32_t parent_node, uint32_t op, int L, const BoundCtx& bc, const DevParams& P) {
+    if (n_hits > 0 && bound_reject_iterative(bc, f.score, best_score)) return;
+    if (f.ngaps > P.max_num_gaps_open) return;
+    uint32_t id;
+    if (free_head != MAPAD_NO_NODE) {  // slab: most recently vacated key first
+      id = free_head;
+      free_head = ws.node(id).parent;
+    } else {
+      id = node_hi;
+      if (!ws.ensure_node(id)) { overflow = true; return; }
+      node_hi += 1;
+    }
+    tree_len += 1;
+    Node nd;
+    node_store(nd, f, parent_node, op);
+    if (f.len == L) {  // a hit: std BinaryHeap::push
+      Grp<G>::sync();
+      if (ws.gl == 0) {
+        ws.node(id) = nd;
+        if (n_hits < MAPAD_MAX_HITS) {
+          HitTmp h;
+          h.score = f.score; h.node = id; h.lower = f.iv.lower; h.lower_rev = f.iv.lower_rev; h.size = f.iv.size;
+          uint32_t nh = n_hits;
+          bh_push(ws.hits, nh, h);
+        }
+      }
+      if (n_hits < MAPAD_MAX_HITS) n_hits += 1;
+      Grp<G>::sync();
+      best_score = ws.hits[0].score;
+      best_size = ws.hits[0].size;
+      return;
+    }
+    if (!ws.ensure_heap(heap_n)) { overflow = true; return; }
+    push(HeapEnt{f.score, id}, nd);
+  }
+
+  // One pop-and-expand step of k_mismatch_search (mapping.rs:1058-1380); same decisions as search_core.cuh::search_step.
+  MAPAD_DEV int step(const DevIndex& ix, const DevParams& P, const SearchJob& job) {
+    const int L = job.L;
+    const BoundCtx& bc = job.bc;
+    const float open_ext = job.open_ext;
+    const uint32_t n = heap_n;
+    if (n == 0) return STEP_DONE;
+    // ---- MinMaxHeap::pop_max ----
+    uint32_t m = 1;
+    if (n == 2) m = 2;
+    else if (n >= 3) m = ws.top[1].score > ws.top[2].score ? 2u : 3u;
+    const HeapEnt topent = ws.top[m - 1u];
+    frames += 1;
+    const Node pn = ws.node(topent.node);  // issued before the heap is repaired: both latencies overlap
+    const uint32_t n1 = n - 1u;
+    if (m <= n1) {
+      const HeapEnt last = rd(n);
+      trickle_max(m, last, n1);
+    }
+    heap_n = n1;
+    Frame sf;
+    node_load(pn, topent.node, sf);
+    sf.score = topent.score;
+    int j, d_k, d_l;
+    bool forward;
+    if (sf.start <= L - sf.start - sf.len) {  // mapping.rs:1077-1097
+      j = sf.start + sf.len; forward = true; d_k = sf.start; d_l = sf.start + sf.len;
+    } else {
+      j = sf.start - 1; forward = false; d_k = sf.start - 1; d_l = sf.start + sf.len - 1;
+    }
+    const PenRow row = job.delta[j];
+    const int side_gap = forward ? sf.gap_f : sf.gap_b;
+    const float insertion_score = fadd(side_gap == GAP_INS ? P.gap_extend : open_ext, sf.score);
+    const float deletion_score = fadd(side_gap == GAP_DEL ? P.gap_extend : open_ext, sf.score);
+    const int num_gaps_open = side_gap == GAP_CLOSED ? sf.ngaps + 1 : sf.ngaps;
+    const float lower_bound = d_get(job.dcomp, L, job.start_pos, d_k, d_l);
+    if (n_hits > 0) {  // mapping.rs:1201-1208
+      if (bound_reject_iterative(bc, fadd(sf.score, lower_bound), best_score)) return STEP_DONE;
+    }
+    const int child_start = forward ? sf.start : sf.start - 1;
+    // candidates in the reference's order (insertion; then for T,G,C,A: deletion, match/mismatch) as 4-bit codes
+    uint64_t codes = 0;
+    int n_cand = 0;
+    {  // insertion (mapping.rs:1213-1242)
+      const int dist = j < L - j - 1 ? j : L - j - 1;
+      if (!bound_reject(bc, fadd(insertion_score, lower_bound)) && dist >= P.gap_dist_ends) { n_cand = 1; }
+    }
+    BiIv ext[4];
+    {
+      const BiIv in = forward ? BiIv{sf.iv.lower_rev, sf.iv.lower, sf.iv.size} : sf.iv;
+      extend_all<WIDE>(ix, in, ext);
+    }
+    const bool del_ok = !bound_reject(bc, fadd(deletion_score, lower_bound));
+    const int dist5 = forward ? j : j + 1;
+    const int dist3 = L - dist5;
+    const bool del_dist_ok = (dist5 < dist3 ? dist5 : dist3) >= P.gap_dist_ends;
+    const uint8_t read_base = job.seq[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ext[k].size < 1) continue;
+      const int pen_idx = forward ? k : 3 - k;  // rank = 4 - k; forward: 4 - rank, backward: rank - 1
+      if (del_ok && del_dist_ok) { codes |= (uint64_t)(4 | k) << (4 * n_cand); n_cand += 1; }
+      const float mm_score = fadd(row.d[pen_idx], sf.score);
+      if (!bound_reject(bc, fadd(mm_score, lower_bound))) { codes |= (uint64_t)(8 | k) << (4 * n_cand); n_cand += 1; }
+    }
+    for (int i = 0; i < n_cand && !overflow; ++i) {
+      const uint32_t code = (uint32_t)(codes >> (4 * i)) & 15u;
+      const uint32_t type = code >> 2, k = code & 3u;
+      Frame ch = sf;
+      uint32_t op;
+      if (type == 0) {
+        ch.start = child_start; ch.len = sf.len + 1;
+        if (forward) ch.gap_f = GAP_INS; else ch.gap_b = GAP_INS;
+        ch.score = insertion_score; ch.ngaps = num_gaps_open;
+        op = pack_op(j, MAPAD_ED_INSERTION, 0);
+      } else {
+        BiIv ip = k == 0 ? ext[0] : (k == 1 ? ext[1] : (k == 2 ? ext[2] : ext[3]));
+        const int rank = 4 - (int)k;
+        uint8_t c;
+        if (forward) { ip = BiIv{ip.lower_rev, ip.lower, ip.size}; c = complement_base(rank_base(rank)); }
+        else c = rank_base(rank);
+        ch.iv = ip;
+        if (type == 1) {
+          if (forward) ch.gap_f = GAP_DEL; else ch.gap_b = GAP_DEL;
+          ch.score = deletion_score; ch.ngaps = num_gaps_open;
+          op = pack_op(j, MAPAD_ED_DELETION, c);
+        } else {
+          const int pen_idx = forward ? (int)k : 3 - (int)k;
+          const float pen = pen_idx == 0 ? row.d[0] : (pen_idx == 1 ? row.d[1] : (pen_idx == 2 ? row.d[2] : row.d[3]));
+          ch.start = child_start; ch.len = sf.len + 1;
+          if (forward) ch.gap_f = GAP_CLOSED; else ch.gap_b = GAP_CLOSED;
+          ch.score = fadd(pen, sf.score);
+          op = c == read_base ? pack_op(j, MAPAD_ED_MATCH, 0) : pack_op(j, MAPAD_ED_MISMATCH, c);
+        }
+      }
+      check_and_push(ch, sf.node, op, L, bc, P);
+    }
+    if (overflow) return STEP_OVERFLOW;
+    // early exits (mapping.rs:1348-1355)
+    if (n_hits > 9 || (n_hits > 0 && best_size > 1)) return STEP_DONE;
+    // limits (mapping.rs:1358-1380): lane 0 runs the sequential MinMaxHeap::pop_min, the result is broadcast
+    if (heap_n > P.stack_limit || tree_len > P.edit_tree_limit) {
+      limit_hit += 1;
+      if (P.stack_limit_abort) return STEP_DONE;
+      const long long e1 = (long long)heap_n - (long long)P.stack_limit;
+      const long long e2 = (long long)tree_len - (long long)P.edit_tree_limit;
+      const long long excess = e1 > e2 ? e1 : e2;
+      for (long long e = 0; e < excess; ++e) {
+        Grp<G>::sync();
+        uint32_t mn_node = 0, popped = 0;
+        if (ws.gl == 0) {
+          HeapEnt mn;
+          uint32_t hn = heap_n;
+          if (mm_pop_min(ws.heap(), hn, mn)) {
+            popped = 1; mn_node = mn.node;
+            if (mn.node != 0) ws.node(mn.node).parent = free_head;  // Tree::remove (backtrack_tree.rs:49-53)
+          }
+        }
+        popped = Grp<G>::shfl(popped, 0);
+        mn_node = Grp<G>::shfl(mn_node, 0);
+        if (popped) {
+          heap_n -= 1;
+          if (mn_node != 0) { free_head = mn_node; tree_len -= 1; }
+        }
+      }
+    }
+    Grp<G>::sync();  // end of step: all writes are visible to the next step's reads
+    return STEP_CONTINUE;
+  }
+};
+
+// The loop of one lane of group `slot` (all G lanes of the group call it with the same arguments but their own `gl`).
+template <bool WIDE, int G, int TOPL>
+MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int gl, HeapEnt* smem_top) {
+  using GS = GroupSearch<WIDE, G, TOPL>;
+  GS gs;
+  auto& ws = gs.ws;
+  ws.pool = a.pool;
+  ws.nt = a.nt; ws.ht = a.ht;
+  ws.table = a.tables + (size_t)slot * (a.nt + a.ht);
+  ws.gl = gl;
+  // group `slot` owns chunks 2 slot (nodes) and 2 slot + 1 (heap) for good; chunks >= 2 n_groups are pooled
+  if (gl == 0) { ws.table[0] = 2 * slot; ws.table[a.nt] = 2 * slot + 1; }
+  ws.n_node_chunks = 1;
+  ws.n_heap_chunks = 1;
+  ws.node0 = reinterpret_cast<typename GS::Node*>(a.pool.base + ((size_t)(2 * slot) << MAPAD_GCHUNK_SHIFT));
+  ws.heap0 = reinterpret_cast<HeapEnt*>(a.pool.base + ((size_t)(2 * slot + 1) << MAPAD_GCHUNK_SHIFT));
+  ws.top = smem_top;
+  ws.hits = a.hit_base + (size_t)slot * MAPAD_MAX_HITS;
+  ws.max_nodes = a.max_nodes;
+  ws.max_heap = a.max_heap;
+  uint32_t busy_iters = 0;
+  bool have = false;
+  uint32_t r = 0;
+  int split = 0;
+  SearchJob job;
+  while (true) {
+    if (!have) {
+      uint32_t w = 0;
+      if (gl == 0) w = dev_atomic_add(&a.cur->queue_head, 1u);
+      w = Grp<G>::shfl(w, 0);
+      if (w >= a.n_work) break;
+      r = a.work_list ? a.work_list[w] : w;
+      const uint64_t o = a.rb.offsets[r];
+      const int L = (int)(a.rb.offsets[r + 1] - o);
+      if (L <= 0) {
+        if (gl == 0) {
+          ReadMid m;
+          m.n_hits = 0; m.hit_off = 0; m.frames_popped = 0; m.flags = 0;
+          a.mid[r] = m;
+        }
+        continue;
+      }
+      split = alignment_start(a.P, a.rb, r, L);
+      job = make_job(a.P, a.bound_table, a.rb.seq + o, L, split, a.delta + o, a.dcomp + o);
+      gs.begin(a.ix, split);
+      have = true;
+    }
+    const int rc = gs.step(a.ix, a.P, job);
+    busy_iters += 1;
+    if (a.iter_budget && busy_iters >= a.iter_budget) break;
+    if (rc == STEP_CONTINUE) continue;
+    have = false;
+    Grp<G>::sync();
+    if (rc == STEP_OVERFLOW) {  // the pool ran dry: the host re-runs the read with fewer groups in flight
+      ws.release_extra();
+      if (gl == 0) a.deferred_list[dev_atomic_add(&a.cur->n_deferred, 1u)] = r;
+      continue;
+    }
+    // ---- emit: lane l traces hits l, l + G, ... back to the root (extract_edit_operations, record.rs:465-500) ----
+    const uint32_t nh = gs.n_hits;
+    uint32_t hit_off = 0;
+    if (nh) {
+      if (gl == 0) hit_off = dev_atomic_add(&a.cur->hit_cursor, nh);
+      hit_off = Grp<G>::shfl(hit_off, 0);
+      for (uint32_t h = (uint32_t)gl; h < nh; h += (uint32_t)G) {
+        const HitTmp ht = ws.hits[h];
+        uint32_t n_left;
+        const uint32_t total = path_length<WIDE>(ws, ht.node, split, n_left);
+        const uint32_t op_off = dev_atomic_add(&a.cur->op_cursor, total);
+        if ((uint64_t)op_off + total <= a.op_cap) path_write<WIDE>(ws, ht.node, split, total, n_left, a.op_pool + op_off);
+        else dev_atomic_or(&a.cur->overflow, 1u);
+        if ((uint64_t)hit_off + h < a.hit_cap) {
+          mapad_hit mh;
+          mh.lower = ht.lower; mh.lower_rev = ht.lower_rev; mh.size = ht.size;
+          mh.alignment_score = ht.score; mh.edit_off = op_off; mh.edit_len = total; mh.reserved = 0;
+          a.hit_pool[hit_off + h] = mh;
+        } else {
+          dev_atomic_or(&a.cur->overflow, 1u);
+        }
+      }
+    }
+    if (gl == 0) {
+      ReadMid m;
+      m.hit_off = hit_off;
+      m.frames_popped = gs.frames;
+      m.flags = (gs.limit_hit ? 1u : 0u) | a.flags_or;
+      m.n_hits = nh;
+      a.mid[r] = m;
+    }
+    Grp<G>::sync();  // the tree is no longer read: its chunks may go back to the pool
+    ws.release_extra();
+  }
+}
+
+#if defined(__CUDACC__)
+#ifndef MAPAD_GROUP_BLOCK
+#define MAPAD_GROUP_BLOCK 128
+#endif
+template <bool WIDE, int G, int TOPL>
+__global__ void __launch_bounds__(MAPAD_GROUP_BLOCK) k_search_group(const __grid_constant__ GroupLaunch<WIDE> a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t group_in_block = threadIdx.x / G;
+  const uint32_t slot = blockIdx.x * (MAPAD_GROUP_BLOCK / G) + group_in_block;
+  HeapEnt* top = reinterpret_cast<HeapEnt*>(smem_raw) + (size_t)group_in_block * TOPL * 8;
+  group_search_lane<WIDE, G, TOPL>(a, slot, (int)(threadIdx.x % G), top);
+}
+
+__global__ void k_gpool_init(GChunkPool p, uint32_t first_free) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n_chunks) p.next[i] = i + 1 < p.n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
+  if (i == 0) *p.head = first_free < p.n_chunks ? (unsigned long long)first_free : (unsigned long long)MAPAD_GPOOL_EMPTY;
+}
+#endif
+
+}  // namespace mapad

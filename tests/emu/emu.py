@@ -14,14 +14,15 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _DEFS = os.environ.get("MAPAD_EMU_DEFS", "").split()
 _LIB = os.path.join(_HERE, "libmapad_emu%s.so" % ("_" + "_".join(d.replace("-D", "").replace("=", "") for d in _DEFS) if _DEFS else ""))
 _lib = None
+SMALL_CHUNKS = any(d.startswith("-DMAPAD_GCHUNK_SHIFT=") for d in _DEFS)  # variant build with tiny pool chunks
 
 
 def build(force=False):
     csrc = os.path.join(_ROOT, "mapad_b200", "csrc")
-    srcs = [os.path.join(_HERE, "emu_harness.cpp")] + [os.path.join(csrc, f) for f in ("host_index.cpp", "host_params.cpp", "dev_index_build.cpp")]
-    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    srcs = [os.path.join(_HERE, "emu_harness.cpp"), os.path.join(_HERE, "simt_emu.cpp")] + [os.path.join(csrc, f) for f in ("host_index.cpp", "host_params.cpp", "dev_index_build.cpp")]
+    deps = srcs + [os.path.join(_HERE, "simt_emu.hpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if os.path.isfile(os.path.join(csrc, f))]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(d) > os.path.getmtime(_LIB) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-o", _LIB] + _DEFS + srcs)
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-march=x86-64-v3", "-shared", "-o", _LIB] + _DEFS + srcs + ["-ldl"])
     return _LIB
 
 
@@ -32,6 +33,9 @@ def lib():
         L = C.CDLL(_LIB)
         L.emu_map_batch.restype = C.c_int
         L.emu_map_batch.argtypes = [C.c_void_p, C.POINTER(abi.Params), C.POINTER(abi.Reads), C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]
+        L.emu_map_batch_group.restype = C.c_int
+        L.emu_map_batch_group.argtypes = [C.c_void_p, C.POINTER(abi.Params), C.POINTER(abi.Reads), C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int,
+                                          C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
         L.emu_batch_view.argtypes = [C.c_void_p, C.POINTER(abi.Results)]
         L.emu_batch_free.argtypes = [C.c_void_p]
         L.emu_occ4.restype = C.c_int
@@ -43,12 +47,21 @@ def lib():
     return _lib
 
 
-def map_batch(index, params, seqs=None, quals=None, seeds=None, cap=1 << 16, layout=-1, packed=None):
+def map_batch(index, params, seqs=None, quals=None, seeds=None, cap=1 << 16, layout=-1, packed=None, group=None):
+    """group=None: the per-thread reference loop (search_core.cuh::search_read); group=dict(G=8, n_groups=3, pool_chunks=64, lpt=1):
+    the group kernel of search_group.cuh under the SIMT emulator."""
     if packed is None:
         packed = abi.pack_reads(seqs, quals)
     R, keep = api.make_reads(packed[0], packed[1], packed[2], seeds)
     h = C.c_void_p()
-    rc = lib().emu_map_batch(index.h, C.byref(params), C.byref(R), cap, layout, C.byref(h))
+    if group is None:
+        rc = lib().emu_map_batch(index.h, C.byref(params), C.byref(R), cap, layout, C.byref(h))
+    else:
+        ng = int(group.get("n_groups", 3))
+        nd = C.c_uint32(0)
+        rc = lib().emu_map_batch_group(index.h, C.byref(params), C.byref(R), layout, int(group.get("G", 8)), ng,
+                                       int(group.get("pool_chunks", 2 * ng + (4096 if SMALL_CHUNKS else 32))), int(group.get("lpt", 1)), C.byref(nd), C.byref(h))
+        map_batch.last_deferred = int(nd.value)
     if rc != 0:
         raise api.MapadError(rc)
     try:

@@ -2,6 +2,7 @@
 // (mapad_b200/csrc/{dev_index,search_core,epilogue_core}.cuh) as plain C++ and runs it one "thread"
 // at a time on the CPU, so that the non-GPU test-suite can check it against the oracle without a
 // device.  It is NOT a product path: the C ABI in libmapad_gpu.so never runs without CUDA.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -10,6 +11,8 @@
 #include "../../mapad_b200/csrc/epilogue_core.cuh"
 #include "../../mapad_b200/csrc/host_index.hpp"
 #include "../../mapad_b200/csrc/host_params.hpp"
+#include "../../mapad_b200/csrc/search_group.cuh"
+#include "simt_emu.hpp"
 
 using namespace mapad;
 
@@ -103,6 +106,145 @@ int run(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, uint32_t
   out.text.resize(text_cur);
   return MAPAD_OK;
 }
+
+// ---- the group kernel (mapad_b200/csrc/search_group.cuh) under the SIMT emulator ----------------
+struct GroupOpts {
+  int group_size;       // G
+  int n_groups;
+  uint32_t pool_chunks; // total chunks incl. the 2 owned per group
+  int lpt;              // 1: longest reads first
+};
+
+template <bool WIDE, int G>
+void launch_groups(const GroupLaunch<WIDE>& a, int n_groups) {
+  constexpr int TOPL = 11;
+  std::vector<HeapEnt> smem((size_t)n_groups * TOPL * 8);
+  if (G == 1) {
+    for (int g = 0; g < n_groups; ++g) group_search_lane<WIDE, 1, TOPL>(a, (uint32_t)g, 0, smem.data() + (size_t)g * TOPL * 8);
+    return;
+  }
+  simt_emu::run(n_groups, G, [&](int g, int l) { group_search_lane<WIDE, G, TOPL>(a, (uint32_t)g, l, smem.data() + (size_t)g * TOPL * 8); });
+}
+
+template <bool WIDE>
+int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, const GroupOpts& go, EmuOut& out, uint32_t* n_deferred_out) {
+  const DevParams& P = bp.dp;
+  const uint64_t n = in.n_reads;
+  const uint64_t base0 = n ? in.offsets[0] : 0;
+  std::vector<uint64_t> offs(n + 1);
+  for (uint64_t r = 0; r <= n; ++r) offs[r] = n ? in.offsets[r] - base0 : 0;
+  ReadBatch rb;
+  rb.n_reads = n; rb.seq = in.seq + base0; rb.qual = in.qual + base0; rb.offsets = offs.data(); rb.seeds = in.seeds;
+  rb.starts = bp.starts.empty() ? nullptr : bp.starts.data();
+  rb.custom_pen = in.custom_penalties ? in.custom_penalties + 4 * base0 : (bp.custom_pen.empty() ? nullptr : bp.custom_pen.data());
+  const uint64_t tb = bp.total_bases;
+  std::vector<PenRow> delta(tb + 1);
+  std::vector<float> dpen(tb + 1), dcomp(tb + 1);
+  std::vector<uint32_t> dsteps(n, 0);
+  for (uint64_t r = 0; r < n; ++r) {
+    const uint64_t o = offs[r];
+    const int L = (int)(offs[r + 1] - o);
+    if (L == 0) continue;
+    for (int j = 0; j < L; ++j) penalty_row(P, bp.qual_table, rb, o, j, L, delta.data(), dpen.data());
+    const int split = alignment_start(P, rb, r, L);
+    for (int half = 0; half < 2; ++half) {
+      const int part_len = half == 0 ? split : L - split;
+      float* dout = dcomp.data() + o + (half == 0 ? 0 : split);
+      if (part_len > 0) dout[0] = 0.0f;
+      DScan sc[15];
+      for (int l = 0; l < 15; ++l) dscan_init<WIDE>(ix, sc[l], l);
+      for (int idx = 0; idx + 1 < part_len; ++idx) {
+        float v = 0.0f;
+        for (int l = 0; l < 15; ++l)
+          if (l <= idx) { dscan_step<WIDE>(ix, sc[l], half, idx, L, rb.seq + o, dpen.data() + o, dsteps[r]); v = fmin_rs(v, sc[l].z); }
+        dout[idx + 1] = v;
+      }
+    }
+  }
+  // launch state
+  const int ng = go.n_groups;
+  const uint32_t n_chunks = go.pool_chunks;
+  if (n_chunks < 2u * (uint32_t)ng) return MAPAD_EINVAL;
+  std::vector<uint8_t> pool_mem((size_t)n_chunks * MAPAD_GCHUNK_BYTES + 64);
+  std::vector<uint32_t> pool_next(n_chunks + 2);
+  unsigned long long pool_head = 2u * (uint32_t)ng < n_chunks ? 2u * (uint32_t)ng : MAPAD_GPOOL_EMPTY;
+  for (uint32_t i = 0; i < n_chunks; ++i) pool_next[i] = i + 1 < n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
+  GroupLaunch<WIDE> a;
+  a.ix = ix; a.P = P; a.rb = rb; a.bound_table = bp.bound_table.data(); a.delta = delta.data(); a.dcomp = dcomp.data();
+  a.pool.base = (uint8_t*)(((uintptr_t)pool_mem.data() + 63) & ~(uintptr_t)63);
+  a.pool.n_chunks = n_chunks; a.pool.head = &pool_head; a.pool.next = pool_next.data();
+  a.max_nodes = P.edit_tree_limit + 64; a.max_heap = P.stack_limit + 64;
+  a.nt = (a.max_nodes >> (MAPAD_GCHUNK_SHIFT - 5)) + 1;
+  a.ht = (heap_lines_for(a.max_heap) >> (MAPAD_GCHUNK_SHIFT - 6)) + 1;
+  std::vector<uint32_t> tables((size_t)ng * (a.nt + a.ht));
+  std::vector<HitTmp> hit_base((size_t)ng * MAPAD_MAX_HITS);
+  a.tables = tables.data(); a.hit_base = hit_base.data();
+  std::vector<uint32_t> work(n), deferred(n + 1);
+  for (uint64_t r = 0; r < n; ++r) work[r] = (uint32_t)r;
+  if (go.lpt) std::stable_sort(work.begin(), work.end(), [&](uint32_t x, uint32_t y) { return offs[x + 1] - offs[x] > offs[y + 1] - offs[y]; });
+  a.work_list = work.data(); a.n_work = (uint32_t)n; a.deferred_list = deferred.data();
+  Cursors cur;
+  memset(&cur, 0, sizeof cur);
+  a.cur = &cur;
+  std::vector<ReadMid> mid(n);
+  a.mid = mid.data();
+  std::vector<mapad_hit> hit_pool(20 * n + 64);
+  std::vector<mapad_edit_op> op_pool(64 + 20 * (tb + 8 * n));
+  a.hit_pool = hit_pool.data(); a.hit_cap = (uint32_t)hit_pool.size();
+  a.op_pool = op_pool.data(); a.op_cap = (uint32_t)op_pool.size();
+  a.iter_budget = 0;
+  a.flags_or = 0;
+  // the host's retry loop (mapad_gpu.cu::search_with_groups): reads handed back because the pool ran dry are re-run
+  // with fewer groups in flight
+  uint32_t total_deferred = 0;
+  int groups_now = ng;
+  std::vector<uint32_t> work2;
+  for (int attempt = 0;; ++attempt) {
+    cur.queue_head = 0; cur.n_deferred = 0;
+    pool_head = 2u * (uint32_t)groups_now < n_chunks ? 2u * (uint32_t)groups_now : MAPAD_GPOOL_EMPTY;
+    for (uint32_t i = 0; i < n_chunks; ++i) pool_next[i] = i + 1 < n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
+    a.flags_or = attempt ? 2u : 0u;
+    switch (go.group_size) {
+      case 1: launch_groups<WIDE, 1>(a, groups_now); break;
+      case 2: launch_groups<WIDE, 2>(a, groups_now); break;
+      case 4: launch_groups<WIDE, 4>(a, groups_now); break;
+      case 8: launch_groups<WIDE, 8>(a, groups_now); break;
+      case 16: launch_groups<WIDE, 16>(a, groups_now); break;
+      case 32: launch_groups<WIDE, 32>(a, groups_now); break;
+      default: return MAPAD_EINVAL;
+    }
+    if (cur.n_deferred == 0) break;
+    total_deferred += cur.n_deferred;
+    if (groups_now == 1 && cur.n_deferred >= a.n_work) { if (n_deferred_out) *n_deferred_out = total_deferred; return MAPAD_ELIMIT; }
+    work2.assign(deferred.begin(), deferred.begin() + cur.n_deferred);
+    a.work_list = work2.data(); a.n_work = cur.n_deferred;
+    groups_now = groups_now > 1 ? groups_now / 2 : 1;
+  }
+  if (n_deferred_out) *n_deferred_out = total_deferred;
+  if (cur.overflow) return MAPAD_ELIMIT;
+  // epilogue
+  out.records.assign(n, mapad_record());
+  out.cigar.assign(64 + 8 * n + 4 * tb, 0);
+  out.text.assign(64 + 16 * n + 8 * tb, 0);
+  uint32_t cig_cur = 0, text_cur = 0, overflow = 0;
+  OutPools pools{out.cigar.data(), (uint32_t)out.cigar.size(), &cig_cur, out.text.data(), (uint32_t)out.text.size(), &text_cur, &overflow};
+  for (uint64_t r = 0; r < n; ++r) {
+    const int L = (int)(offs[r + 1] - offs[r]);
+    mapad_record& rec = out.records[r];
+    memset(&rec, 0, sizeof rec);
+    rec.tid = -1; rec.pos = -1;
+    if (L == 0) continue;
+    const ReadMid m = mid[r];
+    epilogue_read<WIDE>(ix, P, bp.bound_table.data(), L, in.seeds ? in.seeds[r] : 0u, hit_pool.data() + m.hit_off, m.n_hits, op_pool.data(), pools, rec);
+    rec.hit_off = m.hit_off; rec.n_hits = m.n_hits; rec.frames_popped = m.frames_popped; rec.d_ext_steps = dsteps[r]; rec.flags = m.flags;
+  }
+  if (overflow) return MAPAD_ELIMIT;
+  out.hits.assign(hit_pool.begin(), hit_pool.begin() + cur.hit_cursor);
+  out.ops.assign(op_pool.begin(), op_pool.begin() + cur.op_cursor);
+  out.cigar.resize(cig_cur);
+  out.text.resize(text_cur);
+  return MAPAD_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -119,6 +261,24 @@ int emu_map_batch(const mapad_index* index, const mapad_params* params, const ma
   if (rc) return rc;
   EmuOut* out = new EmuOut();
   rc = meta.wide ? run<true>(ix, bp, *in, cap, *out) : run<false>(ix, bp, *in, cap, *out);
+  if (rc) { delete out; return rc; }
+  *out_handle = out;
+  return MAPAD_OK;
+}
+int emu_map_batch_group(const mapad_index* index, const mapad_params* params, const mapad_reads* in, int layout, int group_size,
+                         int n_groups, uint32_t pool_chunks, int lpt, uint32_t* n_deferred_out, void** out_handle) {
+  const HostIndex* hix = reinterpret_cast<const HostIndex*>(index);
+  IndexMeta meta;
+  std::vector<uint8_t> blob;
+  int rc = build_device_blob(*hix, meta, blob, layout);
+  if (rc) return rc;
+  DevIndex ix{meta, blob.data()};
+  BatchPrep bp;
+  rc = prepare_batch(*params, *in, bp);
+  if (rc) return rc;
+  EmuOut* out = new EmuOut();
+  GroupOpts go{group_size, n_groups, pool_chunks, lpt};
+  rc = meta.wide ? run_group<true>(ix, bp, *in, go, *out, n_deferred_out) : run_group<false>(ix, bp, *in, go, *out, n_deferred_out);
   if (rc) { delete out; return rc; }
   *out_handle = out;
   return MAPAD_OK;
