@@ -406,16 +406,13 @@ static int upload_batch(mapad_gpu* h, const mapad_reads* in) {
 // One launch maps every read of the batch; a read is only handed back (deferred) when the chunk pool runs dry, and
 // then re-run with fewer groups in flight, i.e. more pool per group.
 struct GroupShape { int g, topl; };
-static GroupShape group_shape() {
-  static const GroupShape shape = [] {
-    GroupShape s{8, 11};
-    if (const char* e = getenv("MAPAD_GROUP")) s.g = atoi(e);
-    if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 32) s.g = 8;
-    s.topl = s.g == 1 ? 3 : (s.g == 32 ? 43 : 11);
-    if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43) s.topl = t; }
-    return s;
-  }();
-  return shape;
+static GroupShape group_shape() {  // tuning knobs, read per batch: MAPAD_GROUP = lanes per read, MAPAD_TOPL = heap lines in shared memory
+  GroupShape s{8, 11};
+  if (const char* e = getenv("MAPAD_GROUP")) s.g = atoi(e);
+  if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 32) s.g = 8;
+  s.topl = s.g == 1 ? 3 : (s.g == 32 ? 43 : 11);
+  if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43) s.topl = t; }
+  return s;
 }
 
 template <bool WIDE, int G, int TOPL>

@@ -157,11 +157,17 @@ print("deferred", int(sum(1 for r in got.records if r["flags"] & 2)), "limit", i
 """
 
 
-def test_wide_layout_and_retry_lanes(api):
-    """64-bit block layout forced on a small index; tiny first-lane workspace so most reads overflow into
-    the retry lanes; results must not change."""
-    out = _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_POOL_MAX_NODES": "64", "MAPAD_LANE0_CAP": "512"})
-    assert int(out.split("deferred")[1].split()[0]) > 100, out
+def test_wide_layout_and_retry_launch(api):
+    """64-bit block layout forced on a small index, and a chunk pool so small that it runs dry: reads are handed back
+    and re-run with fewer groups in flight; results must not change.  Also every group size the library is built for."""
+    out = _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1"})
+    for g in ("1", "4", "32"):
+        _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_GROUP": g})
+    # 16 groups own 32 of the 72 chunks (256 KiB each); the largest of these reads pops 3e5 frames, so the 40 pooled chunks
+    # run dry while several groups grow at once (calibrated with the emulation: tests/test_group_kernel.py)
+    out = _run_child(CHILD.replace("SPEC_EXTRA", "").replace("(30, 90)", "(50, 70)").replace("genome = random_genome(200000, seed=43)", "genome = random_genome(3000000, seed=43)"),
+                     {"MAPAD_GROUPS": "16", "MAPAD_TEST_POOL_CHUNKS": "72"})
+    assert int(out.split("deferred")[1].split()[0]) > 0, out
 
 
 def test_search_limits_eviction(api):
