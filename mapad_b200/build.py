@@ -13,7 +13,7 @@ HEADERS = ["common.h", "dev_index.cuh", "search_core.cuh", "epilogue_core.cuh", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # exact f32 parity with the reference: never contract a*b+c (every FMA in the source is explicit)
-    "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "static",
+    "--fmad=false", "--Werror", "cross-execution-space-call", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "static",
 ]
 
 

@@ -15,9 +15,11 @@
 #include "common.h"
 
 #if defined(__CUDACC__)
+#define MAPAD_HD __host__ __device__ __forceinline__
 #define MAPAD_DEV __device__ __forceinline__
 #define MAPAD_DEV_NOINLINE __device__ __noinline__
 #else
+#define MAPAD_HD inline
 #define MAPAD_DEV inline
 #define MAPAD_DEV_NOINLINE inline
 #endif

@@ -76,14 +76,21 @@ MAPAD_DEV void gpool_release(const GChunkPool& p, uint32_t idx) {
 // is a CHILD of its owner x >> 1 (slots 0, 1), one on an odd level >= 3 a GRANDCHILD of its owner x >> 2 (slots 2..5).
 // Owners are the positions of odd levels; the owner o of level lo gets line  o - C(lo),  C(lo) = (2^(lo+1) - 1) / 3.
 struct HLoc { uint32_t line, slot; };
-MAPAD_DEV int clz32(uint32_t x) {
+MAPAD_HD int clz32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
   return __clz((int)x);
 #else
   return __builtin_clz(x);
 #endif
 }
-MAPAD_DEV HLoc heap_loc(uint32_t x) {
+MAPAD_DEV int ffs32(uint32_t x) {  // 1-based index of the lowest set bit, 0 if none
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+MAPAD_HD HLoc heap_loc(uint32_t x) {
   if (x < 4u) return HLoc{0u, x - 1u};
   const int lvl = 31 - clz32(x);
   const uint32_t odd = (uint32_t)lvl & 1u;
@@ -94,7 +101,7 @@ MAPAD_DEV HLoc heap_loc(uint32_t x) {
   return HLoc{owner - c, slot};
 }
 // number of lines that positions 1..n occupy
-MAPAD_DEV uint32_t heap_lines_for(uint32_t n) {
+MAPAD_HD uint32_t heap_lines_for(uint32_t n) {
   if (n < 4u) return 1u;
   const int lvl = 31 - clz32(n);
   // the last position of the deepest even level <= lvl decides
@@ -289,33 +296,71 @@ struct GroupSearch {
     wr(hpos, e);
   }
 
-  // MinMaxHeap::push of `e` + Tree::add_node of `nd` at `id` (the two writes of an accepted child).
+  // MinMaxHeap::push of `e` + Tree::add_node of `nd` (the two writes of an accepted child).
+  // The positions a new element can visit depend only on its position x: the parent p = x / 2, then the grandparent chain
+  // of x (the element stays on its level) or of p (it was swapped with the parent).  Cooperative version: every lane reads
+  // the parent, lanes [0, G/2) fetch the chain of x and lanes [G/2, G) the chain of p in the same round trip, a vote finds
+  // where the climb stops, and the lanes whose ancestors move one chain level down write them in parallel.  Deeper chains
+  // (more than G/2 levels) continue with all G lanes on the chosen chain.
   MAPAD_DEV void push(HeapEnt e, const Node& nd) {
     const uint32_t x = heap_n + 1u;
     heap_n = x;
     Grp<G>::sync();  // writes of the previous phase are visible
-    HeapEnt pe = e;
-    bool moved = false;
-    uint32_t t = 0;
-    if (x > 1u) {
-      const uint32_t p = x >> 1;
-      pe = rd(p);
-      const bool min_level = ((31 - clz32(x)) & 1) == 0;
-      moved = min_level ? (e.score > pe.score) : (e.score < pe.score);
+    if (x == 1u) {
+      if (ws.gl == 0) { ws.node(e.node) = nd; ws.top[0] = e; }
+      return;
+    }
+    const uint32_t p = x >> 1;
+    const bool min_level = ((31 - clz32(x)) & 1) == 0;
+    if (G == 1) {  // sequential: count the steps first, then move the ancestors down
+      const HeapEnt pe = rd(p);
+      const bool moved = min_level ? (e.score > pe.score) : (e.score < pe.score);
       const bool climb_max = min_level == moved;
-      uint32_t c = moved ? p : x;
-      while (c >= 4u) {  // count the grandparent steps; nothing is written yet
+      uint32_t t = 0, c = moved ? p : x;
+      while (c >= 4u) {
         const HeapEnt ae = rd(c >> 2);
         if (climb_max ? (e.score > ae.score) : (e.score < ae.score)) { t += 1; c >>= 2; } else break;
       }
-    }
-    Grp<G>::sync();  // every lane has finished reading
-    if (ws.gl == 0) {
       ws.node(e.node) = nd;
       uint32_t cur = x;
-      if (moved) { *ptr(x) = pe; cur = x >> 1; }
+      if (moved) { *ptr(x) = pe; cur = p; }
       for (uint32_t k = 0; k < t; ++k) { *ptr(cur) = *ptr(cur >> 2); cur >>= 2; }
       *ptr(cur) = e;
+      return;
+    }
+    constexpr int H = G > 1 ? G / 2 : 1;
+    const int gl = ws.gl;
+    const bool in_b = gl >= H;
+    const uint32_t lvl = (uint32_t)(in_b ? gl - H : gl) + 1u;          // chain level of this lane in round 1
+    const uint32_t anc = lvl < 16u ? (in_b ? p : x) >> (2u * lvl) : 0u;  // 1-based position of that grandparent, 0 = none
+    HeapEnt v = e;
+    if (anc) v = rd(anc);
+    const HeapEnt pe = rd(p);
+    const bool moved = min_level ? (e.score > pe.score) : (e.score < pe.score);
+    const bool climb_max = min_level == moved;
+    const bool wins = anc != 0u && (climb_max ? (e.score > v.score) : (e.score < v.score));
+    const uint32_t ball = Grp<G>::ballot(wins);  // also: every lane has finished reading
+    const uint32_t half = moved ? (ball >> H) : (ball & ((1u << H) - 1u));
+    const uint32_t t1 = (uint32_t)ffs32(~half) - 1u;                     // leading run of winning levels (<= H)
+    const uint32_t cur0 = moved ? p : x;
+    if (anc != 0u && in_b == moved && lvl <= t1) *ptr(cur0 >> (2u * (lvl - 1u))) = v;
+    uint32_t total = t1, base = (uint32_t)H;
+    while (total == base && base < 16u && (cur0 >> (2u * base)) >= 4u) {  // every fetched level won and the chain goes on
+      const uint32_t l2 = base + (uint32_t)gl + 1u;
+      const uint32_t a2 = l2 < 16u ? cur0 >> (2u * l2) : 0u;
+      HeapEnt v2 = e;
+      if (a2) v2 = rd(a2);
+      const bool w2 = a2 != 0u && (climb_max ? (e.score > v2.score) : (e.score < v2.score));
+      const uint32_t b2 = Grp<G>::ballot(w2);
+      const uint32_t t2 = b2 == 0xffffffffu ? 32u : (uint32_t)ffs32(~b2) - 1u;
+      if (a2 != 0u && (uint32_t)gl < t2) *ptr(cur0 >> (2u * (l2 - 1u))) = v2;
+      total += t2;
+      base += (uint32_t)G;
+    }
+    if (gl == 0) {
+      ws.node(e.node) = nd;
+      if (moved) *ptr(x) = pe;
+      *ptr(cur0 >> (2u * total)) = e;
     }
   }
 

@@ -57,7 +57,7 @@ def main():
         if lib:
             e["MAPAD_GPU_LIB"] = lib
         err = open(os.path.join(ROOT, "gpurun_out", "ab_%s.err" % name), "w")
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-cpu-baseline"],
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-cpu-baseline", "--workload", os.environ.get("AB_WORKLOAD", "cfg3")],
                            env=e, cwd=ROOT, stdout=subprocess.PIPE, stderr=err, text=True, timeout=900)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
         open(os.path.join(ROOT, "gpurun_out", "ab_%s.json" % name), "w").write(line + "\n")
