@@ -259,6 +259,16 @@ int mapad_gpu_copy_index_to(mapad_gpu* h, void* dst_dev_ptr, uint64_t dst_bytes)
 int mapad_gpu_create_from_device_blob(const void* meta, void* dev_ptr, uint64_t dev_bytes, int take_ownership,
                                       const mapad_index* contigs_and_symbols, const mapad_params* params,
                                       int device, mapad_gpu** out);
+/* Single-process multi-GPU: a second handle for `device`.  On the source handle's own GPU the resident index blob is
+ * shared; on another GPU of the box it is replicated with ONE peer-to-peer copy (NVLink) — the in-process counterpart of
+ * the NCCL broadcast above.  Replaces the per-worker index loading of the reference's worker farm
+ * (/root/reference/src/distributed/worker.rs:45-215) for single-box runs; the caller shards each chunk of reads over the
+ * handles and merges the results in input order like the dispatcher (src/distributed/dispatcher.rs:341-379). */
+int mapad_gpu_clone_to_device(mapad_gpu* src, int device, mapad_gpu** out);
+/* Announces how many handles the caller is about to create on `device`: each then sizes its search workspace (the chunk
+ * pool the per-read heaps / edit trees grow in — the thread-local scratch of mapping.rs:146-149) to an equal share of the
+ * free device memory instead of the single-handle default.  MAPAD_WS_BYTES overrides both. */
+int mapad_gpu_plan_handles(int device, int n_handles);
 int mapad_gpu_set_params(mapad_gpu* h, const mapad_params* params);
 int mapad_gpu_map_batch(mapad_gpu* h, const mapad_reads* in, uint32_t flags, mapad_results* out);
 /* Uses the caller's CUDA stream (a cudaStream_t cast to void*) for all subsequent work; NULL = own stream. */

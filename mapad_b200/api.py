@@ -57,6 +57,8 @@ def lib():
             "mapad_gpu_export_index": (i32, [vp, vp, P(vp), P(u64)]),
             "mapad_gpu_copy_index_to": (i32, [vp, vp, u64]),
             "mapad_gpu_create_from_device_blob": (i32, [vp, vp, u64, i32, vp, P(abi.Params), i32, P(vp)]),
+            "mapad_gpu_clone_to_device": (i32, [vp, i32, P(vp)]),
+            "mapad_gpu_plan_handles": (i32, [i32, i32]),
             "mapad_gpu_set_params": (i32, [vp, P(abi.Params)]),
             "mapad_gpu_map_batch": (i32, [vp, P(abi.Reads), u32, P(abi.Results)]),
             "mapad_gpu_set_stream": (i32, [vp, vp]),
@@ -93,7 +95,7 @@ EXPORTED_SYMBOLS = [
     "mapad_abi_version", "mapad_abi_sizeof", "mapad_params_from_cli", "mapad_sdm_get", "mapad_sdm_representative_mismatch_penalty",
     "mapad_bound_allowed_mismatches", "mapad_index_build", "mapad_index_build_on_device", "mapad_index_build_with_draws", "mapad_index_from_view",
     "mapad_index_get_view", "mapad_index_free", "mapad_index_save", "mapad_index_load", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
-    "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_set_params", "mapad_gpu_map_batch",
+    "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_clone_to_device", "mapad_gpu_plan_handles", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
     "mapad_fastq_open", "mapad_fastq_next_chunk", "mapad_fastq_close", "mapad_chunk_view", "mapad_chunk_free", "mapad_bam_open",
     "mapad_bam_write_chunk", "mapad_bam_close", "mapad_input_open", "mapad_input_is_bam", "mapad_input_header_text", "mapad_input_next_chunk",
@@ -228,6 +230,11 @@ def make_reads(seq, qual, offsets, seeds=None, custom_penalties=None):
     return R, keep
 
 
+def plan_handles(device, n_handles):
+    """Tell the library how many handles are about to be created on `device` (workspace = equal shares of free memory)."""
+    _check(lib().mapad_gpu_plan_handles(device, n_handles))
+
+
 class Mapper:
     """One GPU-resident index + parameters; maps batches of reads (one in flight per handle)."""
 
@@ -280,13 +287,16 @@ class Mapper:
         return cls(index, params, device, _handle=out)
 
     def clone(self, device=None):
-        """A second handle on the same device that shares this handle's GPU-resident index blob (no copy).
-        Handles are independent otherwise (own stream, workspace, one batch in flight each), which lets a
-        driver keep several chunks in flight so that straggler reads of one chunk overlap with the next."""
-        meta, ptr, nbytes = self.export_index()
-        c = Mapper.from_device_blob(meta, ptr, nbytes, self.index, self.params, self.device if device is None else device,
-                                    take_ownership=False)
-        c._blob_owner = self  # keep the owner alive
+        """A second handle.  On this handle's own device it shares the GPU-resident index blob (no copy); on another
+        GPU of the box the blob is replicated with one peer-to-peer copy.  Handles are independent otherwise (own
+        stream, workspace, one batch in flight each), which lets a driver keep several chunks in flight — straggler
+        reads of one chunk overlap with the next — and shard chunks over several GPUs."""
+        device = self.device if device is None else device
+        out = C.c_void_p()
+        _check(lib().mapad_gpu_clone_to_device(self.h, device, C.byref(out)), self.h)
+        c = Mapper(self.index, self.params, device, _handle=out)
+        if device == self.device:
+            c._blob_owner = self  # keep the owner of the shared blob alive
         return c
 
     def map_raw(self, reads_struct, flags=0):

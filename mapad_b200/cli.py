@@ -66,8 +66,9 @@ def build_parser():
     m.add_argument("--force_overwrite", action="store_true")
     m.add_argument("-R", "--read_group", default=None, help="read group ID added to every record")
     m.add_argument("--seed", type=int, default=1234)
-    m.add_argument("--device", type=int, default=0)
-    m.add_argument("--inflight", type=int, default=4)
+    m.add_argument("--device", type=int, default=0, help="first CUDA device")
+    m.add_argument("--gpus", type=int, default=1, help="shard every chunk of reads over this many GPUs of the box (devices --device ..)")
+    m.add_argument("--inflight", type=int, default=8, help="chunks kept in flight per GPU")
     ix = sub.add_parser("index", help="Indexes a genome file")
     ix.add_argument("-g", "--reference", required=True, help="FASTA file of the genome")
     ix.add_argument("--seed", type=int, default=1234)
@@ -97,6 +98,22 @@ def params_from_args(a):
                                ignore_base_quality=a.ignore_base_quality, no_search_limit_recovery=a.no_search_limit_recovery)
 
 
+class _Shard:
+    """A contiguous range [lo, hi) of a chunk's reads as its own mapad_reads view (pointers advanced, nothing copied)."""
+
+    def __init__(self, R, names, noff, flags, lo, hi, seeds):
+        self.R = abi.Reads()
+        self.R.n_reads = hi - lo
+        self.R.seq, self.R.qual = R.seq, R.qual
+        self.R.offsets = R.offsets + 8 * lo
+        self.seeds = np.ascontiguousarray(seeds[lo:hi])
+        self.R.seeds = self.seeds.ctypes.data
+        self.names = names
+        self.noff = C.c_void_p(noff.value + 8 * lo) if noff.value else noff
+        self.flags = C.c_void_p(flags.value + 2 * lo) if flags.value else flags
+        self.lo, self.hi = lo, hi
+
+
 def run_map(a, argv):
     params = params_from_args(a)
     if os.path.exists(a.reference + ".tbw"):
@@ -104,56 +121,100 @@ def run_map(a, argv):
     else:
         print("no index files next to %s: indexing in memory" % a.reference, file=sys.stderr)
         index = build_index(a.reference, a.seed, None)
-    first = api.Mapper(index, params, device=a.device)
-    mappers = [first] + [first.clone() for _ in range(max(1, a.inflight) - 1)]
+    # one set of `inflight` handles per GPU; the index is re-laid-out once and replicated with one peer copy per further GPU
+    devices = [a.device + d for d in range(max(1, a.gpus))]
+    inflight = max(1, a.inflight)
+    for d in devices:
+        api.plan_handles(d, inflight)
+    firsts = [api.Mapper(index, params, device=devices[0])]
+    firsts += [firsts[0].clone(device=d) for d in devices[1:]]
+    pools = [[f] + [f.clone() for _ in range(inflight - 1)] for f in firsts]
     chunks = api.ReadChunks(a.reads, a.batch_size)
     writer = api.BamWriter(a.output, index, command_line=" ".join(argv), read_group_id=a.read_group, force_overwrite=a.force_overwrite,
                            src_header_text=chunks.header_text)
     rng = np.random.default_rng(a.seed)
-    done = {}
+    state = dict(next=0, mapped=0, reads=0, error=None)
     lock = threading.Condition()
-    jobs = queue.Queue(maxsize=len(mappers))
-    n_reads = n_mapped = 0
+    queues = [queue.Queue(maxsize=inflight) for _ in devices]
+    pending = {}  # chunk k -> [shards still to be written, chunk handle]
 
-    def worker(mp):
+    def worker(mp, q):
+        # every shard has a sequence number; results (valid until this handle's next call) are written in that order.
+        # After a failure the workers keep draining their queues without mapping, so that nobody waits forever.
         while True:
-            job = jobs.get()
+            job = q.get()
             if job is None:
                 return
-            k, (R, names, noff, flags, n, ch), seeds = job
-            R.seeds = seeds.ctypes.data
-            res = mp.map_raw(R, 0)
-            # results stay valid until this handle's next call: write them under the ordering lock
-            with lock:
-                while done.get("next", 0) != k:
-                    lock.wait()
-                writer.write_chunk(R, names, noff, flags, res, chunk=ch)
-                recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
-                done["mapped"] = done.get("mapped", 0) + int(recs["mapped"].sum())
-                done["reads"] = done.get("reads", 0) + n
-                done["next"] = k + 1
-                lock.notify_all()
-            chunks.free(ch)
+            seqno, k, sh, aux, aoff = job
+            try:
+                res = None
+                if state["error"] is None:
+                    res = mp.map_raw(sh.R, 0)
+                with lock:
+                    while state["next"] != seqno and state["error"] is None:
+                        lock.wait()
+                    if state["error"] is None:
+                        api._check(api.lib().mapad_bam_write_chunk_aux(writer.w, index.h, C.byref(sh.R), sh.names, sh.noff, sh.flags, aux, aoff, C.byref(res)))
+                        recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
+                        state["mapped"] += int(recs["mapped"].sum())
+                        state["reads"] += sh.hi - sh.lo
+                        state["next"] = seqno + 1
+                        lock.notify_all()
+            except Exception as e:  # noqa: BLE001
+                with lock:
+                    if state["error"] is None:
+                        state["error"] = e
+                    lock.notify_all()
+            finally:
+                with lock:
+                    pending[k][0] -= 1
+                    if pending[k][0] == 0:
+                        chunks.free(pending.pop(k)[1])
 
-    threads = [threading.Thread(target=worker, args=(mp,)) for mp in mappers]
+    threads = [threading.Thread(target=worker, args=(mp, queues[d])) for d in range(len(devices)) for mp in pools[d]]
     for t in threads:
         t.start()
-    k = 0
-    for item in chunks:
-        seeds = rng.integers(0, 1 << 32, size=item[4], dtype=np.uint64).astype(np.uint32)
-        jobs.put((k, item, seeds))
-        k += 1
-    for _ in threads:
-        jobs.put(None)
-    for t in threads:
-        t.join()
-    writer.close()
+    from .sharding import shard_range
+    seqno = k = 0
+    try:
+        for R, names, noff, flags, n, ch in chunks:
+            if state["error"] is not None:
+                chunks.free(ch)
+                break
+            seeds = rng.integers(0, 1 << 32, size=n, dtype=np.uint64).astype(np.uint32)
+            aux, aoff = C.c_void_p(), C.c_void_p()
+            api._check(api.lib().mapad_chunk_aux(ch, C.byref(aux), C.byref(aoff)))
+            ranges = [shard_range(n, d, len(devices)) for d in range(len(devices))]
+            ranges = [(d, lo, hi) for d, (lo, hi) in enumerate(ranges) if hi > lo]
+            with lock:
+                pending[k] = [len(ranges), ch]
+            for d, lo, hi in ranges:
+                sh = _Shard(R, names, noff, flags, lo, hi, seeds)
+                sh_aoff = C.c_void_p(aoff.value + 8 * lo) if aoff.value else aoff
+                queues[d].put((seqno, k, sh, aux, sh_aoff))
+                seqno += 1
+            k += 1
+    finally:
+        for d in range(len(devices)):
+            for _ in pools[d]:
+                queues[d].put(None)
+        for t in threads:
+            t.join()
+    err = state["error"]
+    try:
+        writer.close()
+    except Exception as e:  # noqa: BLE001
+        err = err or e
     chunks.close()
-    n_reads, n_mapped = done.get("reads", 0), done.get("mapped", 0)
-    print("mapped %d of %d reads (%d skipped on input)" % (n_mapped, n_reads, chunks.skipped), file=sys.stderr)
-    for mp in mappers[1:]:
-        mp.close()
-    first.close()
+    for pool in pools:
+        for mp in pool[1:]:
+            mp.close()
+    for f in reversed(firsts):
+        f.close()
+    if err is not None:
+        print("mapad_b200: mapping failed: %s" % err, file=sys.stderr)
+        return 1
+    print("mapped %d of %d reads (%d skipped on input)" % (state["mapped"], state["reads"], chunks.skipped), file=sys.stderr)
     return 0
 
 

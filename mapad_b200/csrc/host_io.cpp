@@ -500,6 +500,7 @@ int mapad_bam_write_chunk_aux(void* writer, const mapad_index* index, const mapa
     const bool has_name = names && name_offsets[r + 1] > name_offsets[r];  // a missing name is written as "*"
     const char* nm = has_name ? names + name_offsets[r] : "*";
     const size_t nml = has_name ? (size_t)(name_offsets[r + 1] - name_offsets[r]) : 1;
+    if (nml > 254) return MAPAD_EINVAL;  // l_read_name is one byte incl. the NUL (noodles rejects such names as well)
     uint16_t flag = in_flags ? in_flags[r] : 0;
     flag &= (uint16_t)~(0x8 | 0x20 | 0x2 | 0x100 | 0x800);                 // :750-755
     if (m.mapped) flag &= (uint16_t)~0x4; else { flag |= 0x4; flag &= (uint16_t)~(0x10 | 0x2); }  // :757-769

@@ -246,12 +246,28 @@ static int init_handle(mapad_gpu* h, int device) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  return MAPAD_OK;
+}
+
+// The search workspace (chunk pool) is allocated after the index blob.  Its size: MAPAD_WS_BYTES, else the share set with
+// mapad_gpu_plan_handles (free memory / planned handles), else a third of the free device memory; at most 48 GiB.
+static int g_planned_handles[64] = {0};  // per device
+static int alloc_workspace(mapad_gpu* h) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const char* env = getenv("MAPAD_WS_BYTES");
-  size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : std::min<size_t>(free_b / 3, (size_t)48 << 30);
+  int& planned = g_planned_handles[h->device & 63];
+  size_t budget;
+  if (env) budget = (size_t)strtoull(env, nullptr, 10);
+  else if (planned > 0) budget = std::min<size_t>((size_t)(free_b * 0.85 / planned), (size_t)48 << 30);
+  else budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
+  if (planned > 0) planned -= 1;
   h->ws_budget = std::max<size_t>(budget, (size_t)64 << 20);
-  CK(h->d_ws.reserve(h->ws_budget + 4096, true));  // one allocation up front: lanes only partition it
+  if (h->ws_budget + ((size_t)256 << 20) > free_b) {
+    h->err = "not enough free device memory for the search workspace (lower MAPAD_WS_BYTES or the number of handles)";
+    return MAPAD_ENOMEM;
+  }
+  CK(h->d_ws.reserve(h->ws_budget + 4096, true));  // one allocation up front: the kernels only partition it
   return MAPAD_OK;
 }
 
@@ -277,6 +293,8 @@ int mapad_gpu_create(const mapad_index* index, const mapad_params* params, int d
   h->own_blob = true;
   e = cudaMemcpy(h->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { mapad_gpu_destroy(h); return MAPAD_ECUDA; }
+  rc = alloc_workspace(h);
+  if (rc) { fprintf(stderr, "mapad_gpu_create: %s\n", h->err.c_str()); mapad_gpu_destroy(h); return rc; }
   *out = h;
   return MAPAD_OK;
 }
@@ -315,7 +333,44 @@ int mapad_gpu_create_from_device_blob(const void* meta, void* dev_ptr, uint64_t 
   h->params = *params;
   h->d_blob = (uint8_t*)dev_ptr;
   h->own_blob = take_ownership != 0;
+  rc = alloc_workspace(h);
+  if (rc) { h->own_blob = false; mapad_gpu_destroy(h); return rc; }
   *out = h;
+  return MAPAD_OK;
+}
+
+int mapad_gpu_clone_to_device(mapad_gpu* src, int device, mapad_gpu** out) {
+  if (!src || !out) return MAPAD_EINVAL;
+  *out = nullptr;
+  std::string err;
+  int rc = pick_device(device, err);
+  if (rc) return rc;
+  mapad_gpu* h = new (std::nothrow) mapad_gpu();
+  if (!h) return MAPAD_ENOMEM;
+  rc = init_handle(h, device);
+  if (rc) { src->err = h->err; mapad_gpu_destroy(h); return rc; }
+  h->meta = src->meta;
+  h->params = src->params;
+  if (device == src->device) {  // same GPU: share the resident blob
+    h->d_blob = src->d_blob;
+    h->own_blob = false;
+  } else {  // another GPU of the box: one peer copy of the re-laid-out blob (NVLink when peer access exists)
+    if (cudaMalloc(&h->d_blob, h->meta.total_bytes) != cudaSuccess) { mapad_gpu_destroy(h); return MAPAD_ENOMEM; }
+    h->own_blob = true;
+    if (cudaMemcpyPeer(h->d_blob, device, src->d_blob, src->device, h->meta.total_bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+      mapad_gpu_destroy(h);
+      return MAPAD_ECUDA;
+    }
+  }
+  rc = alloc_workspace(h);
+  if (rc) { src->err = h->err; mapad_gpu_destroy(h); return rc; }
+  *out = h;
+  return MAPAD_OK;
+}
+
+int mapad_gpu_plan_handles(int device, int n_handles) {
+  if (device < 0 || device >= 64) return MAPAD_EINVAL;
+  g_planned_handles[device] = n_handles > 0 ? n_handles : 0;
   return MAPAD_OK;
 }
 
