@@ -131,7 +131,8 @@ typedef struct mapad_index_view {
 int mapad_index_build(uint64_t n_contigs, const char* const* names, const char* const* sequences,
                       const uint64_t* lengths, uint64_t seed, mapad_index** out);
 /* Same result, but the suffix sorting runs on CUDA device `device` (prefix-key radix sort; falls back to the host
- * SA-IS for texts in which two suffixes share a 43-symbol prefix).  Needed for hg19-scale references. */
+ * SA-IS for texts in which two suffixes share a 43-symbol prefix, i.e. for every real genome: repeats, N runs >= 20 bp).
+ * It is what makes the hg19-scale SYNTHETIC (i.i.d.) BASELINE reference indexable in a minute. */
 int mapad_index_build_on_device(uint64_t n_contigs, const char* const* names, const char* const* sequences,
                                 const uint64_t* lengths, uint64_t seed, int device, mapad_index** out);
 /* Same, but ambiguous symbols in short runs are replaced by the bytes of `replacement_draws`

@@ -143,7 +143,8 @@ class Index:
     @classmethod
     def build(cls, contigs, seed=1234, draws=None, device=None):
         """`mapad index` on in-memory contigs: list[(name, sequence)] (src/index/indexing.rs:29-212).
-        device=k: suffix sorting on CUDA device k (required in practice for hg19-scale references)."""
+        device=k: suffix sorting on CUDA device k.  That sorter finishes only texts in which no two suffixes share a 43-symbol
+        prefix (the i.i.d. synthetic BASELINE genomes); real genomes (repeats, N runs) fall back to the host SA-IS automatically."""
         n = len(contigs)
         names = (C.c_char_p * n)(*[c[0].encode() if isinstance(c[0], str) else c[0] for c in contigs])
         seqs_b = [c[1].encode() if isinstance(c[1], str) else bytes(c[1]) for c in contigs]

@@ -72,15 +72,14 @@ def build_parser():
     ix = sub.add_parser("index", help="Indexes a genome file")
     ix.add_argument("-g", "--reference", required=True, help="FASTA file of the genome")
     ix.add_argument("--seed", type=int, default=1234)
-    ix.add_argument("--device", type=int, default=None, help="sort suffixes on this CUDA device (default: only above 0.5 Gbp)")
+    ix.add_argument("--device", type=int, default=None, help="sort suffixes on this CUDA device (tie-free synthetic texts only; default: host SA-IS)")
     return ap
 
 
 def build_index(path, seed, device):
     contigs = read_fasta(path)
-    total = sum(len(c[1]) for c in contigs)
-    if device is None and total > 500_000_000:
-        device = 0
+    # device=None: host SA-IS.  The device suffix sorter (--device) only finishes tie-free texts (synthetic i.i.d. genomes);
+    # it is never chosen automatically for FASTA input, because real genomes make it fall back to the host after a wasted pass.
     return api.Index.build(contigs, seed=seed, device=device)
 
 

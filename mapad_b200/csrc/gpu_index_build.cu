@@ -200,8 +200,19 @@ int gpu_suffix_sort(const std::vector<uint8_t>& ranks, int device, HostIndex& ix
     unsigned int n_extra = 0;
     GK(cudaMemcpy(&ties, d_ties, 8, cudaMemcpyDeviceToHost));
     GK(cudaMemcpy(&n_extra, d_n_extra, 4, cudaMemcpyDeviceToHost));
-    if (ties != 0 || row0 != n || n_extra > 16) {
-      fprintf(stderr, "gpu_index_build: %llu suffix pairs share a 43-symbol prefix (repetitive text): use the host builder\n", ties);
+    if (ties != 0) {
+      fprintf(stderr, "gpu_index_build: %llu suffix pairs share a 43-symbol prefix (repeats, N runs >= 20, or palindromic fwd/revcomp "
+                      "stretches: any real genome) — this sorter only finishes texts without such ties; falling back to the host SA-IS\n", ties);
+      rc = MAPAD_EINDEX;
+      goto done;
+    }
+    if (row0 != n) {
+      fprintf(stderr, "gpu_index_build: internal error: %llu of %llu rows produced\n", (unsigned long long)row0, (unsigned long long)n);
+      rc = MAPAD_EINDEX;
+      goto done;
+    }
+    if (n_extra > 16) {
+      fprintf(stderr, "gpu_index_build: %u unsampled sentinel rows (expected at most 2)\n", n_extra);
       rc = MAPAD_EINDEX;
       goto done;
     }

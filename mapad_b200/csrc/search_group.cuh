@@ -296,6 +296,44 @@ struct GroupSearch {
     wr(hpos, e);
   }
 
+  // MinMaxHeap::trickle_down_min from the root (pop_min, used by the limit recovery of mapping.rs:1358-1380): the node at a
+  // min level looks at its two children and four grandchildren, which the family layout spreads over three lines (the
+  // children sit in the line the node itself lives in); all six are fetched in one round trip by every lane.
+  MAPAD_DEV void trickle_min(HeapEnt e, uint32_t n) {
+    uint32_t h = 1u;
+    bool synced = false;
+    while (2u * h <= n) {
+      HeapEnt x[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
+        x[c] = e;
+        if (idx <= n) x[c] = rd(idx);
+      }
+      Grp<G>::sync();
+      synced = true;
+      int best = -1;
+      float bk = e.score;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
+        if (idx <= n && x[c].score < bk) { best = c; bk = x[c].score; }
+      }
+      if (best < 0) break;
+      HeapEnt be = x[0];
+#pragma unroll
+      for (int c = 1; c < 6; ++c) if (best == c) be = x[c];
+      wr(ptr(h), be);
+      if (best < 2) { h = 2u * h + (uint32_t)best; break; }
+      const int pc = (best - 2) >> 1;
+      const HeapEnt pe = pc == 0 ? x[0] : x[1];
+      h = 4u * h + (uint32_t)(best - 2);
+      if (pe.score < e.score) { wr(ptr(h >> 1), e); e = pe; }
+    }
+    if (!synced) Grp<G>::sync();
+    wr(ptr(h), e);
+  }
+
   // MinMaxHeap::push of `e` + Tree::add_node of `nd` (the two writes of an accepted child).
   // The positions a new element can visit depend only on its position x: the parent p = x / 2, then the grandparent chain
   // of x (the element stays on its level) or of p (it was swapped with the parent).  Cooperative version: every lane reads
@@ -514,29 +552,27 @@ struct GroupSearch {
     if (overflow) return STEP_OVERFLOW;
     // early exits (mapping.rs:1348-1355)
     if (n_hits > 9 || (n_hits > 0 && best_size > 1)) return STEP_DONE;
-    // limits (mapping.rs:1358-1380): lane 0 runs the sequential MinMaxHeap::pop_min, the result is broadcast
+    // limits (mapping.rs:1358-1380): evict the worst frames (MinMaxHeap::pop_min) and their tree nodes
     if (heap_n > P.stack_limit || tree_len > P.edit_tree_limit) {
       limit_hit += 1;
       if (P.stack_limit_abort) return STEP_DONE;
       const long long e1 = (long long)heap_n - (long long)P.stack_limit;
       const long long e2 = (long long)tree_len - (long long)P.edit_tree_limit;
       const long long excess = e1 > e2 ? e1 : e2;
-      for (long long e = 0; e < excess; ++e) {
+      for (long long e = 0; e < excess && heap_n > 0; ++e) {  // MinMaxHeap::pop_min + Tree::remove, every lane in step
         Grp<G>::sync();
-        uint32_t mn_node = 0, popped = 0;
-        if (ws.gl == 0) {
-          HeapEnt mn;
-          uint32_t hn = heap_n;
-          if (mm_pop_min(ws.heap(), hn, mn)) {
-            popped = 1; mn_node = mn.node;
-            if (mn.node != 0) ws.node(mn.node).parent = free_head;  // Tree::remove (backtrack_tree.rs:49-53)
-          }
+        const HeapEnt mn = ws.top[0];
+        const uint32_t n1 = heap_n - 1u;
+        if (n1 > 0u) {
+          const HeapEnt last = rd(heap_n);
+          trickle_min(last, n1);
         }
-        popped = Grp<G>::shfl(popped, 0);
-        mn_node = Grp<G>::shfl(mn_node, 0);
-        if (popped) {
-          heap_n -= 1;
-          if (mn_node != 0) { free_head = mn_node; tree_len -= 1; }
+        heap_n = n1;
+        if (mn.node != 0u) {  // Tree::remove (backtrack_tree.rs:49-53): the vacated key heads the slab's free list
+          Grp<G>::sync();
+          if (ws.gl == 0) ws.node(mn.node).parent = free_head;
+          free_head = mn.node;
+          tree_len -= 1;
         }
       }
     }

@@ -179,6 +179,106 @@ def test_search_limits_eviction(api):
     assert int(out.split("limit")[1].split()[0]) > 20, out
 
 
+def test_cfg3_size_index(api):
+    """The benchmarked cfg3 index itself (50 Mbp, 8 contigs, host SA-IS) with reads simulated exactly like bench.py's chunks."""
+    from mapad_b200 import workloads
+    cfg = workloads.CONFIGS["cfg3"]
+    genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
+    index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234)
+    oix = oracle_index_from_product(index)
+    spec = cli_params(cfg["library"])
+    n = 4000
+    packed = workloads.simulate_batch(genome, n, cfg["len_range"], seed=cfg["seed"] * 1000 + 20_000, library=cfg["library"])
+    seeds = np.arange(n, dtype=np.uint32)
+    want = ora.map_batch(oix, oracle_params(spec), None, None, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=True, packed=packed)
+    m = api.Mapper(index, product_params(spec))
+    got = m.map_batch(seeds=seeds, want_hits=True, packed=packed)
+    m.close()
+    compare_results(want, got)
+    assert got.records["mapped"].mean() > 0.8 and got.records["tid"].max() == 7
+
+
+def test_continuous_bound(api):
+    """Continuous mismatch bound (-c / -e of older mapAD versions, mismatch_bounds.rs:77-121) on the device."""
+    genome = random_genome(1_000_000, seed=5)
+    index = api.Index.build([("c1", genome[:400_000]), ("c2", genome[400_000:])])
+    oix = oracle_index_from_product(index)
+    spec = dict(cli_params("single_stranded"))
+    spec["bound"] = ("continuous", -0.25, 1.0)
+    seqs, quals = simulate_reads(genome, 1500, (25, 80), seed=17)
+    seeds = np.arange(len(seqs), dtype=np.uint32)
+    want = ora.map_batch(oix, oracle_params(spec), seqs, quals, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=True)
+    m = api.Mapper(index, product_params(spec))
+    got = m.map_batch(seqs, quals, seeds=seeds, want_hits=True)
+    m.close()
+    compare_results(want, got)
+    assert 0.3 < got.records["mapped"].mean() <= 1.0
+
+
+def test_cfg5_cell(api):
+    """One cell of the BASELINE cfg5 stress sweep (L = 100, -p 0.06: k(100) = 7 allowed mismatches) on a small index, so that
+    the oracle finishes in seconds: deep heaps, pool growth and (with the small limits of the second pass) eviction."""
+    genome = random_genome(1_500_000, seed=9)
+    index = api.Index.build([("c", genome)])
+    oix = oracle_index_from_product(index)
+    spec = dict(cli_params("single_stranded"))
+    spec["bound"] = ("discrete", 0.06, 0.02)
+    seqs, quals = simulate_reads(genome, 300, (100, 100), seed=23)
+    seeds = np.arange(len(seqs), dtype=np.uint32)
+    m = api.Mapper(index, product_params(spec))
+    for limits in (None, (3000, 9000)):
+        if limits:
+            spec["limits"] = limits
+            m.set_params(product_params(spec))
+        want = ora.map_batch(oix, oracle_params(spec), seqs, quals, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=True)
+        got = m.map_batch(seqs, quals, seeds=seeds, want_hits=True)
+        compare_results(want, got)
+    assert sum(1 for r in got.records if r["flags"] & 1) > 5
+    m.close()
+
+
+def test_real_wide_index(api):
+    """A reference whose text (2 G + 2 symbols) exceeds 2^32 rows: device suffix sorter, 64-byte occ blocks, u64 SA samples,
+    40-bit tree nodes.  Reads from both strands, reads that straddle a contig boundary (must not be reported there), and
+    rows / positions beyond 2^32."""
+    from mapad_b200 import workloads
+    gbp = 2_200_000_000
+    genome = workloads.random_genome_array(gbp, seed=42)
+    contigs = workloads.split_contigs(genome, 24)
+    index = api.Index.build(contigs, device=0)
+    a = index.arrays()
+    assert a["n"] == 2 * gbp + 2 and a["n"] > 1 << 32
+    oix = ora.OracleIndex.from_arrays(a["bwt"], a["sa_sample"], a["sa_rate"], a["extra_rows"], a["contigs"], a["orig_pos"], a["orig_sym"])
+    del a
+    spec = cli_params("single_stranded")
+    n = 260
+    seq, qual, off = workloads.simulate_batch(genome, n, (25, 60), seed=77)
+    # 20 undamaged reads across contig boundaries (10 per strand): their only exact locus straddles two contigs
+    cuts = [gbp * i // 24 for i in range(25)]  # workloads.split_contigs
+    comp = {65: 84, 67: 71, 71: 67, 84: 65}
+    for k in range(20):
+        L = int(off[k + 1] - off[k])
+        b = cuts[k % 23 + 1]  # boundary between contig (k % 23) and the next
+        w = genome[b - L // 2: b - L // 2 + L].copy()
+        if k % 2:
+            w = np.array([comp[int(c)] for c in w[::-1]], dtype=np.uint8)
+        seq[int(off[k]):int(off[k + 1])] = w
+        qual[int(off[k]):int(off[k + 1])] = 40
+    seeds = np.arange(n, dtype=np.uint32)
+    want = ora.map_batch(oix, oracle_params(spec), None, None, seeds=seeds, n_threads=os.cpu_count() or 4, want_hits=True, packed=(seq, qual, off))
+    m = api.Mapper(index, product_params(spec))
+    got = m.map_batch(seeds=seeds, want_hits=True, packed=(seq, qual, off))
+    m.close()
+    compare_results(want, got)
+    rec = got.records
+    assert int(rec["best_lower"].max()) > 1 << 32 and int(rec["absolute_pos"].max()) > 1 << 31
+    assert rec["strand"][rec["mapped"] != 0].sum() > 20
+    for k in range(20):  # never reported at the locus it was cut from
+        if rec["mapped"][k]:
+            L = int(off[k + 1] - off[k])
+            assert abs(int(rec["absolute_pos"][k]) - (cuts[k % 23 + 1] - L // 2)) > L, k
+
+
 def test_device_index_builder_matches_host(api):
     """mapad_index_build_on_device (prefix-key radix sort on the GPU) must produce exactly the arrays of the host
     SA-IS builder; a repetitive text makes it fall back to the host builder (still identical)."""
