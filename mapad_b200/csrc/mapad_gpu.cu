@@ -520,6 +520,7 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
   uint32_t n_work = (uint32_t)n;
   const uint32_t* work = h->d_order.p;
   uint32_t* deferred = h->d_deferred_a.p;
+  bool serial = false;  // last resort: one read per launch, i.e. the whole pool for a single group
   for (int attempt = 0; n_work > 0; ++attempt) {
     uint64_t use = std::min<uint64_t>(slots, ((uint64_t)n_work + gpb - 1) / gpb * gpb);
     use = use / gpb * gpb;
@@ -536,25 +537,32 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
     a.pool.head = reinterpret_cast<unsigned long long*>(h->d_pool_next.p);
     a.tables = h->d_pool_tables.p;
     a.hit_base = h->d_pool_hits.p;
-    a.work_list = work; a.n_work = n_work; a.deferred_list = deferred;
     a.cur = h->d_cur.p; a.mid = h->d_mid.p;
     a.hit_pool = h->d_hits.p; a.hit_cap = (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu);
     a.op_pool = h->d_ops.p; a.op_cap = (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu);
     a.iter_budget = profile_iters;
     a.flags_or = attempt ? 2u : 0u;
-    k_gpool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(a.pool, (uint32_t)(2 * use));
-    ++launches;
-    CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter
-    CK(launch_group_dispatch<WIDE>(sh, a, (uint32_t)use, h->stream));
-    ++launches;
-    CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaGetLastError());
-    if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the search was cut short for profiling, no results"; return MAPAD_ELIMIT; }
-    const uint32_t n_def = h->h_cur.p->n_deferred;
-    trace("group", n_work, n_def, use);
+    a.deferred_list = deferred;
+    uint32_t n_def = 0;
+    const uint32_t n_launches = serial ? n_work : 1u;
+    for (uint32_t l = 0; l < n_launches; ++l) {
+      a.work_list = serial ? work + l : work;
+      a.n_work = serial ? 1u : n_work;
+      k_gpool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(a.pool, (uint32_t)(2 * use));
+      ++launches;
+      CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter
+      CK(launch_group_dispatch<WIDE>(sh, a, (uint32_t)use, h->stream));
+      ++launches;
+      CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      CK(cudaGetLastError());
+      if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the search was cut short for profiling, no results"; return MAPAD_ELIMIT; }
+      n_def = h->h_cur.p->n_deferred;
+      if (serial && n_def) { h->err = "a read exceeded the search workspace even with the whole pool to itself"; return MAPAD_ELIMIT; }
+    }
+    trace(serial ? "group (one read per launch)" : "group", n_work, n_def, use);
     if (n_def == 0) break;
-    if (use <= gpb && n_def >= n_work) { h->err = "reads exceeded the search workspace even with the smallest number of groups in flight"; return MAPAD_ELIMIT; }
+    if (use <= gpb && n_def >= n_work) serial = true;  // no progress with the smallest grid: the reads block each other
     work = deferred;
     deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
     n_work = n_def;

@@ -235,6 +235,21 @@ struct GroupLaunch {
 // write phase that follows it (and between a write phase and the next read phase).  For G = 1 the barriers vanish and
 // this is a plain per-thread search.
 // ---------------------------------------------------------------------------------------------
+// Speculative prefetch of the heap lines the NEXT trickle-down step may need (it depends on which grandchild wins): with
+// at least four lanes per read, lane b asks for the family line of grandchild b while the current step is being decided,
+// so a descent through the pooled (HBM / L2) levels costs one memory latency per TWO steps.  Costs up to 4x the line
+// traffic of those levels; build with -DMAPAD_TRICKLE_PREFETCH=0 to compare.
+#ifndef MAPAD_TRICKLE_PREFETCH
+#define MAPAD_TRICKLE_PREFETCH 1
+#endif
+MAPAD_DEV void prefetch_line(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 struct HeapLine6 { HeapEnt x[6]; };
 MAPAD_DEV HeapLine6 load_line6(const HeapEnt* ln) {  // three aligned 16-byte loads
   HeapLine6 r;
@@ -272,6 +287,11 @@ struct GroupSearch {
     while (2u * h <= n) {
       HeapEnt* ln = ws.line_ptr(h - c_lo);
       const HeapLine6 f = load_line6(ln);
+      if (MAPAD_TRICKLE_PREFETCH && G >= 4 && ws.gl < 4) {
+        const uint32_t g = 4u * h + (uint32_t)ws.gl;             // grandchild gl of h; its family line is needed if it has children
+        const uint32_t gline = g - ((c_lo << 2) | 1u);
+        if (2u * g <= n && gline >= (uint32_t)TOPL) prefetch_line(ws.line_ptr(gline));
+      }
       Grp<G>::sync();  // every lane holds the line (and everything read before) — lane 0 may write now
       synced = true;
       int best = -1;
@@ -309,6 +329,14 @@ struct GroupSearch {
         const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
         x[c] = e;
         if (idx <= n) x[c] = rd(idx);
+      }
+      if (MAPAD_TRICKLE_PREFETCH && G >= 8 && ws.gl < 8) {
+        // the next step (at one of the four grandchildren g) reads the two family lines of g's children: eight candidates
+        const uint32_t child = 2u * (4u * h + ((uint32_t)ws.gl >> 1)) + ((uint32_t)ws.gl & 1u);
+        if (2u * child <= n) {
+          const uint32_t cline = heap_loc(2u * child).line;
+          if (cline >= (uint32_t)TOPL) prefetch_line(ws.line_ptr(cline));
+        }
       }
       Grp<G>::sync();
       synced = true;

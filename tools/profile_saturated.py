@@ -1,8 +1,8 @@
-"""Launches ONE k_search_pool over a cfg3 chunk with every resident thread busy and a fixed number of expansions per
-thread (MAPAD_PROFILE_ITERS), i.e. the saturated phase only, short enough for ncu:
+"""Launches ONE k_search_group over a chunk of reads on the cfg3 index with every resident group busy and a fixed number
+of expansions per group (MAPAD_PROFILE_ITERS), i.e. the saturated phase only, short enough for ncu:
 
-    ncu --set full --clock-control none --import-source on -k regex:k_search_pool -c 1 -o gpurun_out/pool_saturated \\
-        python tools/profile_saturated.py
+    MAPAD_GROUP=8 ncu --set full --clock-control none --import-source on -k regex:k_search_group -c 1 -o gpurun_out/r2_g8 \\
+        python tools/profile_saturated.py [min_len max_len]     # default 50 50 (cfg3); 86 100 = heavy reads, deep heaps
 
 The batch is discarded by the library (MAPAD_ELIMIT) — this is a profiling aid, not a product path."""
 import os
@@ -13,8 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ.setdefault("MAPAD_POOL_THREADS", str(148 * 4 * 128))
-os.environ.setdefault("MAPAD_WS_BYTES", str(120 << 30))
+os.environ.setdefault("MAPAD_WS_BYTES", str(60 << 30))
 os.environ.setdefault("MAPAD_PROFILE_ITERS", "3000")
 from mapad_b200 import api, workloads  # noqa: E402
 from helpers import product_params  # noqa: E402
@@ -24,7 +23,8 @@ cfg = workloads.CONFIGS["cfg3"]
 genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
 index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234, device=0)
 mapper = api.Mapper(index, product_params(cli_params(cfg["library"])), device=0)
-seq, qual, off = workloads.simulate_batch(genome, 250_000, cfg["len_range"], seed=79, library=cfg["library"])
+len_range = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else cfg["len_range"]
+seq, qual, off = workloads.simulate_batch(genome, 250_000, len_range, seed=79, library=cfg["library"])
 R, keep = api.make_reads(seq, qual, off, np.arange(250_000, dtype=np.uint32))
 try:
     mapper.map_raw(R, 0)
