@@ -294,10 +294,6 @@ int mapad_input_is_bam(void* reader);
 const char* mapad_input_header_text(void* reader); /* SAM header text of a BAM input, NULL otherwise */
 int mapad_input_next_chunk(void* reader, uint64_t max_reads, void** chunk_out);
 void mapad_input_close(void* reader);
-/* older names of the same three calls */
-int mapad_fastq_open(const char* path, void** reader_out);
-int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out);
-void mapad_fastq_close(void* reader);
 uint64_t mapad_chunk_view(void* chunk, mapad_reads* reads, const char** names, const uint64_t** name_offsets,
                           const uint16_t** flags, uint64_t* skipped);
 /* raw BAM auxiliary fields of the chunk's reads: read i owns aux[aux_offsets[i] .. aux_offsets[i+1]) */

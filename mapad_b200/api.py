@@ -74,9 +74,6 @@ def lib():
             "mapad_chunk_aux": (i32, [vp, P(vp), P(vp)]),
             "mapad_bam_open_with_header": (i32, [C.c_char_p, vp, C.c_char_p, C.c_char_p, i32, C.c_char_p, P(vp)]),
             "mapad_bam_write_chunk_aux": (i32, [vp, vp, P(abi.Reads), vp, vp, vp, vp, vp, P(abi.Results)]),
-            "mapad_fastq_open": (i32, [C.c_char_p, P(vp)]),
-            "mapad_fastq_next_chunk": (i32, [vp, u64, P(vp)]),
-            "mapad_fastq_close": (None, [vp]),
             "mapad_chunk_view": (u64, [vp, P(abi.Reads), P(vp), P(vp), P(vp), P(u64)]),
             "mapad_chunk_free": (None, [vp]),
             "mapad_bam_open": (i32, [C.c_char_p, vp, C.c_char_p, C.c_char_p, i32, P(vp)]),
@@ -97,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "mapad_index_get_view", "mapad_index_free", "mapad_index_save", "mapad_index_load", "mapad_format_xa", "mapad_gpu_create", "mapad_gpu_index_meta_size",
     "mapad_gpu_export_index", "mapad_gpu_copy_index_to", "mapad_gpu_create_from_device_blob", "mapad_gpu_clone_to_device", "mapad_gpu_plan_handles", "mapad_gpu_set_params", "mapad_gpu_map_batch",
     "mapad_gpu_set_stream", "mapad_gpu_last_error", "mapad_gpu_destroy", "mapad_gpu_gather_peak", "mapad_gpu_debug_libm",
-    "mapad_fastq_open", "mapad_fastq_next_chunk", "mapad_fastq_close", "mapad_chunk_view", "mapad_chunk_free", "mapad_bam_open",
+    "mapad_chunk_view", "mapad_chunk_free", "mapad_bam_open",
     "mapad_bam_write_chunk", "mapad_bam_close", "mapad_input_open", "mapad_input_is_bam", "mapad_input_header_text", "mapad_input_next_chunk",
     "mapad_input_close", "mapad_chunk_aux", "mapad_bam_open_with_header", "mapad_bam_write_chunk_aux",
 ]

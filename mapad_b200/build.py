@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmapad_gpu.so")
 SOURCES = ["mapad_gpu.cu", "gpu_index_build.cu", "host_index.cpp", "host_params.cpp", "dev_index_build.cpp", "host_io.cpp", "host_index_files.cpp"]
 HEADERS = ["common.h", "dev_index.cuh", "search_core.cuh", "epilogue_core.cuh", "libm_emu.cuh", "host_index.hpp",
-           "host_params.hpp", "dev_index_build.hpp", "sais.hpp", "search_pool.cuh", "search_warp.cuh", "search_group.cuh", "simt.cuh", "../../include/mapad_gpu.h"]
+           "host_params.hpp", "dev_index_build.hpp", "sais.hpp", "search_group.cuh", "simt.cuh", "../../include/mapad_gpu.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -256,7 +256,6 @@ int mapad_input_open(const char* path, void** out) {
   *out = r;
   return MAPAD_OK;
 }
-int mapad_fastq_open(const char* path, void** out) { return mapad_input_open(path, out); }
 int mapad_input_is_bam(void* reader) { return reader && ((InputReader*)reader)->is_bam ? 1 : 0; }
 // SAM header text of a BAM input (NULL for FASTQ); valid until the reader is closed.
 const char* mapad_input_header_text(void* reader) {
@@ -321,7 +320,7 @@ static int bam_next_chunk(InputReader* r, uint64_t max_reads, ReadChunk* c) {
 
 // Reads up to `max_reads` records (the reference's --batch_size chunking, input_chunk_reader.rs:176-244); records whose
 // sequence and quality lengths differ or that are longer than i16::MAX are skipped like there (:200-214, record.rs:188).
-int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) {
+int mapad_input_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) {
   if (!reader || !chunk_out) return MAPAD_EINVAL;
   InputReader* r = (InputReader*)reader;
   ReadChunk* c = new (std::nothrow) ReadChunk();
@@ -358,12 +357,10 @@ int mapad_fastq_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) {
   *chunk_out = c;
   return MAPAD_OK;
 }
-int mapad_input_next_chunk(void* reader, uint64_t max_reads, void** chunk_out) { return mapad_fastq_next_chunk(reader, max_reads, chunk_out); }
-void mapad_fastq_close(void* reader) {
+void mapad_input_close(void* reader) {
   InputReader* r = (InputReader*)reader;
   if (r) { if (r->f) gzclose(r->f); delete r; }
 }
-void mapad_input_close(void* reader) { mapad_fastq_close(reader); }
 // Raw BAM auxiliary fields of the chunk's reads: read i owns aux[aux_offsets[i] .. aux_offsets[i+1]).
 int mapad_chunk_aux(void* chunk, const uint8_t** aux, const uint64_t** aux_offsets) {
   ReadChunk* c = (ReadChunk*)chunk;

@@ -3,9 +3,9 @@
 // Kernel inventory (SURVEY.md §2 "New sm_100a kernels"):
 //   k_penalties   K1a  penalty rows: SimpleAncientDnaModel::get on the device, optimal scores
 //   k_darray      K1b  BiDArray::new: 15 offset scans per read, one scan per lane of a 16-lane group
-//   k_search_pool K2   k_mismatch_search, throughput lane (search_pool.cuh): persistent threads, one read per thread in a
-//                      flat loop, dynamic read queue, min-max heap + edit tree in pooled 64 KiB HBM chunks
-//   k_search_warp K2   k_mismatch_search, heavy-tail lanes (search_warp.cuh): one read per warp, heap top in shared memory
+//   k_search_group K2  k_mismatch_search (search_group.cuh): persistent lane groups (G lanes per read), one flat loop, dynamic
+//                      read queue (longest reads first), min-max heap in 64-byte family lines (top in shared memory) and
+//                      edit tree in 256 KiB chunks of a device-wide pool; reads are never restarted
 //   k_epilogue    K3   intervals_to_bam: best hit, SA locate, strand / contig, MAPQ, CIGAR / MD / NM, alts
 //   k_gather      roofline denominator: independent random sector gathers
 // There is no CPU fallback: every entry point fails with MAPAD_ENODEV without a CUDA device.
@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -24,8 +25,6 @@
 #include "dev_index_build.hpp"
 #include "epilogue_core.cuh"
 #include "search_group.cuh"
-#include "search_pool.cuh"
-#include "search_warp.cuh"
 #include "host_index.hpp"
 #include "host_params.hpp"
 
@@ -171,8 +170,23 @@ struct PinBuf {  // grow-only pinned host buffer
 
 }  // namespace
 
+// Device-wide search workspace: ONE pool of 256 KiB chunks per GPU, shared by every handle (and every launch in flight) of
+// the process — the per-read heaps and edit trees of all chunks in flight grow in it, so that memory goes where the heavy
+// reads are instead of being partitioned per handle.  Created with the first handle on a device, freed with the last.
+namespace {
+struct DeviceArena {
+  uint8_t* base = nullptr;
+  uint32_t* next = nullptr;   // [0..1]: Treiber head (64 bit), [2..]: next pointers
+  uint64_t n_chunks = 0;
+  int refs = 0;
+};
+std::mutex g_arena_mu;
+DeviceArena g_arena[64];
+}  // namespace
+
 struct mapad_gpu {
   int device = 0;
+  DeviceArena* arena = nullptr;
   int n_sm = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -194,12 +208,10 @@ struct mapad_gpu {
   DevBuf<uint32_t> d_dsteps, d_deferred_a, d_deferred_b;
   DevBuf<ReadMid> d_mid;
   DevBuf<Cursors> d_cur;
-  DevBuf<uint8_t> d_ws;  // workspace pool shared by all lanes
-  DevBuf<uint32_t> d_pool_next, d_pool_tables;
+  DevBuf<uint32_t> d_pool_tables;    // chunk tables of the groups of one launch
   DevBuf<uint32_t> d_order;          // read ids, longest first (work list of the group kernel)
   PinBuf<uint32_t> h_order;
   DevBuf<HitTmp> d_pool_hits;
-  DevBuf<unsigned long long> d_lane_stats;
   DevBuf<mapad_hit> d_hits;
   DevBuf<mapad_edit_op> d_ops;
   DevBuf<uint32_t> d_cigar;
@@ -249,26 +261,50 @@ static int init_handle(mapad_gpu* h, int device) {
   return MAPAD_OK;
 }
 
-// The search workspace (chunk pool) is allocated after the index blob.  Its size: MAPAD_WS_BYTES, else the share set with
-// mapad_gpu_plan_handles (free memory / planned handles), else a third of the free device memory; at most 48 GiB.
+// The search workspace (chunk pool) is allocated after the first index blob of the device.  Size: MAPAD_WS_BYTES, else 75 %
+// of the free device memory minus 0.5 GiB per handle announced with mapad_gpu_plan_handles (their batch buffers).
 static int g_planned_handles[64] = {0};  // per device
 static int alloc_workspace(mapad_gpu* h) {
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  const char* env = getenv("MAPAD_WS_BYTES");
-  int& planned = g_planned_handles[h->device & 63];
-  size_t budget;
-  if (env) budget = (size_t)strtoull(env, nullptr, 10);
-  else if (planned > 0) budget = std::min<size_t>((size_t)(free_b * 0.85 / planned), (size_t)48 << 30);
-  else budget = std::min<size_t>(free_b / 3, (size_t)48 << 30);
-  if (planned > 0) planned -= 1;
-  h->ws_budget = std::max<size_t>(budget, (size_t)64 << 20);
-  if (h->ws_budget + ((size_t)256 << 20) > free_b) {
-    h->err = "not enough free device memory for the search workspace (lower MAPAD_WS_BYTES or the number of handles)";
-    return MAPAD_ENOMEM;
+  std::lock_guard<std::mutex> lock(g_arena_mu);
+  DeviceArena& ar = g_arena[h->device & 63];
+  if (ar.refs == 0) {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const char* env = getenv("MAPAD_WS_BYTES");
+    size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : (size_t)(free_b * 0.75);
+    if (!env) {
+      const size_t reserve = (size_t)g_planned_handles[h->device & 63] << 29;
+      if (budget + reserve > (size_t)(free_b * 0.9)) budget = (size_t)(free_b * 0.9) > reserve ? (size_t)(free_b * 0.9) - reserve : 0;
+    }
+    budget = std::max<size_t>(budget, (size_t)64 << 20);
+    if (budget + ((size_t)128 << 20) > free_b) {
+      h->err = "not enough free device memory for the search workspace (lower MAPAD_WS_BYTES)";
+      return MAPAD_ENOMEM;
+    }
+    uint64_t n_chunks = budget >> MAPAD_GCHUNK_SHIFT;
+    if (const char* e = getenv("MAPAD_TEST_POOL_CHUNKS")) n_chunks = std::min<uint64_t>(n_chunks, strtoull(e, nullptr, 10));  // test hook: tiny pool
+    CK(cudaMalloc(&ar.base, (n_chunks << MAPAD_GCHUNK_SHIFT) + 4096));
+    if (cudaMalloc(&ar.next, (n_chunks + 2) * sizeof(uint32_t)) != cudaSuccess) { cudaFree(ar.base); ar.base = nullptr; h->err = "cudaMalloc(pool links)"; return MAPAD_ENOMEM; }
+    ar.n_chunks = n_chunks;
+    GChunkPool pool;
+    pool.base = ar.base; pool.n_chunks = (uint32_t)n_chunks; pool.next = ar.next + 2; pool.head = reinterpret_cast<unsigned long long*>(ar.next);
+    k_gpool_init<<<(unsigned)((n_chunks + 255) / 256), 256>>>(pool, 0u);
+    CK(cudaDeviceSynchronize());
   }
-  CK(h->d_ws.reserve(h->ws_budget + 4096, true));  // one allocation up front: the kernels only partition it
+  ar.refs += 1;
+  h->arena = &ar;
+  h->ws_budget = (size_t)ar.n_chunks << MAPAD_GCHUNK_SHIFT;
   return MAPAD_OK;
+}
+static void release_workspace(mapad_gpu* h) {
+  if (!h->arena) return;
+  std::lock_guard<std::mutex> lock(g_arena_mu);
+  DeviceArena& ar = *h->arena;
+  h->arena = nullptr;
+  if (--ar.refs == 0) {
+    cudaFree(ar.base); cudaFree(ar.next);
+    ar.base = nullptr; ar.next = nullptr; ar.n_chunks = 0;
+  }
 }
 
 extern "C" {
@@ -395,10 +431,11 @@ void mapad_gpu_destroy(mapad_gpu* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->own_blob && h->d_blob) cudaFree(h->d_blob);
+  release_workspace(h);
   h->d_seq.release(); h->d_qual.release(); h->d_offsets.release(); h->d_seeds.release(); h->d_starts.release();
   h->d_custom.release(); h->d_bound.release(); h->d_qualtab.release(); h->d_dpen.release(); h->d_dcomp.release();
   h->d_delta.release(); h->d_dsteps.release(); h->d_deferred_a.release(); h->d_deferred_b.release(); h->d_mid.release();
-  h->d_cur.release(); h->d_ws.release(); h->d_pool_next.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_lane_stats.release(); h->d_order.release(); h->h_order.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
+  h->d_cur.release(); h->d_pool_tables.release(); h->d_pool_hits.release(); h->d_order.release(); h->h_order.release(); h->d_hits.release(); h->d_ops.release(); h->d_cigar.release(); h->d_text.release();
   h->d_records.release();
   h->h_seq.release(); h->h_qual.release(); h->h_offsets.release(); h->h_seeds.release(); h->h_records.release();
   h->h_hits.release(); h->h_ops.release(); h->h_cigar.release(); h->h_text.release(); h->h_cur.release();
@@ -508,19 +545,21 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
   a.max_heap = P.stack_limit + 64u;
   a.nt = (a.max_nodes >> (MAPAD_GCHUNK_SHIFT - 5u)) + 1u;
   a.ht = (heap_lines_for(a.max_heap) >> (MAPAD_GCHUNK_SHIFT - 6u)) + 1u;
-  uint64_t n_chunks = h->ws_budget >> MAPAD_GCHUNK_SHIFT;
-  if (const char* e = getenv("MAPAD_TEST_POOL_CHUNKS")) n_chunks = std::min<uint64_t>(n_chunks, strtoull(e, nullptr, 10));  // test hook: tiny pool
-  // resident groups per SM: 16 warps of G = 8 lanes (64 reads); per-thread mode: 512 threads
+  const DeviceArena& ar = *h->arena;
+  const uint64_t n_chunks = ar.n_chunks;
+  // resident groups per SM: 16 warps (G = 8: 64 reads per SM); per-thread mode: 512 threads
   uint64_t per_sm = sh.g == 1 ? 512 : (sh.g == 32 ? 16 : (uint64_t)(512 / sh.g));
   if (const char* e = getenv("MAPAD_GROUPS_PER_SM")) per_sm = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
   uint64_t slots = per_sm * (uint64_t)h->n_sm;
   if (const char* e = getenv("MAPAD_GROUPS")) slots = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
-  slots = std::min<uint64_t>(slots, n_chunks / 4);  // two owned chunks per group, at least half of the pool for growth
+  slots = std::min<uint64_t>(slots, n_chunks / 4);  // two base chunks per group, at least half of the pool for growth
   const uint32_t profile_iters = getenv("MAPAD_PROFILE_ITERS") ? (uint32_t)strtoul(getenv("MAPAD_PROFILE_ITERS"), nullptr, 0) : 0u;
   uint32_t n_work = (uint32_t)n;
   const uint32_t* work = h->d_order.p;
   uint32_t* deferred = h->d_deferred_a.p;
-  bool serial = false;  // last resort: one read per launch, i.e. the whole pool for a single group
+  // A read is handed back (deferred) when the shared pool stays dry for longer than the read's patience.  Deferred reads are
+  // re-run with fewer groups of this handle in flight; the last resort is one read per launch that waits for the pool.
+  bool serial = false;
   for (int attempt = 0; n_work > 0; ++attempt) {
     uint64_t use = std::min<uint64_t>(slots, ((uint64_t)n_work + gpb - 1) / gpb * gpb);
     use = use / gpb * gpb;
@@ -528,13 +567,12 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
       if (n_chunks < 2ull * gpb + 2) { h->err = "search workspace does not fit the device memory budget"; return MAPAD_ELIMIT; }
       use = gpb;
     }
-    CK(h->d_pool_next.reserve(n_chunks + 2));
     CK(h->d_pool_tables.reserve(use * (size_t)(a.nt + a.ht)));
     CK(h->d_pool_hits.reserve(use * MAPAD_MAX_HITS));
-    a.pool.base = h->d_ws.p;
+    a.pool.base = ar.base;
     a.pool.n_chunks = (uint32_t)n_chunks;
-    a.pool.next = h->d_pool_next.p + 2;
-    a.pool.head = reinterpret_cast<unsigned long long*>(h->d_pool_next.p);
+    a.pool.next = ar.next + 2;
+    a.pool.head = reinterpret_cast<unsigned long long*>(ar.next);
     a.tables = h->d_pool_tables.p;
     a.hit_base = h->d_pool_hits.p;
     a.cur = h->d_cur.p; a.mid = h->d_mid.p;
@@ -542,21 +580,21 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
     a.op_pool = h->d_ops.p; a.op_cap = (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu);
     a.iter_budget = profile_iters;
     a.flags_or = attempt ? 2u : 0u;
+    a.patient = serial ? 1u : 0u;
     a.deferred_list = deferred;
     uint32_t n_def = 0;
     const uint32_t n_launches = serial ? n_work : 1u;
     for (uint32_t l = 0; l < n_launches; ++l) {
       a.work_list = serial ? work + l : work;
       a.n_work = serial ? 1u : n_work;
-      k_gpool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(a.pool, (uint32_t)(2 * use));
-      ++launches;
       CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter
-      CK(launch_group_dispatch<WIDE>(sh, a, (uint32_t)use, h->stream));
+      CK(launch_group_dispatch<WIDE>(sh, a, (uint32_t)(serial ? gpb : use), h->stream));
       ++launches;
       CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
       CK(cudaStreamSynchronize(h->stream));
       CK(cudaGetLastError());
       if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the search was cut short for profiling, no results"; return MAPAD_ELIMIT; }
+      if (h->h_cur.p->overflow & MAPAD_POOL_TIMEOUT_FLAG) { h->err = "the device-wide chunk pool stayed empty for 20 s (workspace too small for the reads in flight)"; return MAPAD_ELIMIT; }
       n_def = h->h_cur.p->n_deferred;
       if (serial && n_def) { h->err = "a read exceeded the search workspace even with the whole pool to itself"; return MAPAD_ELIMIT; }
     }
@@ -579,7 +617,6 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
   // MAPAD_TRACE=1: host-clock timeline of the lanes of every batch on stderr (tuning aid)
   static const int trace_level = getenv("MAPAD_TRACE") ? atoi(getenv("MAPAD_TRACE")) : 0;  // 1: timeline, 2: + lane utilisation
   static const bool trace_on = trace_level > 0;
-  static const bool trace_stats = trace_level > 1;
   static const auto trace_epoch = std::chrono::steady_clock::now();
   auto now_s = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - trace_epoch).count(); };
   double trace_t0 = trace_on ? now_s() : 0.0;
@@ -624,137 +661,9 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     CK(h->d_hits.reserve(hit_cap)); CK(h->d_ops.reserve(op_cap)); CK(h->d_cigar.reserve(cig_cap)); CK(h->d_text.reserve(text_cap));
     CK(cudaMemsetAsync(h->d_cur.p, 0, sizeof(Cursors), h->stream));
     // ---- K2: search ----
-    static const bool legacy_search = getenv("MAPAD_SEARCH") && !strcmp(getenv("MAPAD_SEARCH"), "legacy");
-    if (!legacy_search) {
+    {
       const int rc = search_with_groups<WIDE>(h, ix, P, rb, launches, trace);
       if (rc) return rc;
-    } else {
-    // ---- K2: search, lane by lane (warp per read; reads that outgrow a lane's workspace move to the next) ----
-    const size_t per_entry = sizeof(HeapEnt) + sizeof(NodeT<WIDE>);
-    const uint64_t full_cap = (uint64_t)std::max(P.stack_limit, P.edit_tree_limit) + 32;
-    uint32_t n_work = (uint32_t)n;
-    const uint32_t* work = nullptr;
-    uint32_t* deferred = h->d_deferred_a.p;
-    uint64_t cap = 65536;
-    const char* cap_env = getenv("MAPAD_LANE0_CAP");
-    if (cap_env) cap = std::max<uint64_t>(2, strtoull(cap_env, nullptr, 10));
-    const char* hs_env = getenv("MAPAD_SMEM_HEAP");
-    // ---- throughput lane: one read per THREAD, workspaces grown in 64 KiB chunks from a pool that spans the whole
-    //      workspace budget; reads that outgrow `max_nodes` restart in the warp-cooperative lanes below ----
-    {
-      const uint32_t profile_iters = getenv("MAPAD_PROFILE_ITERS") ? (uint32_t)strtoul(getenv("MAPAD_PROFILE_ITERS"), nullptr, 0) : 0u;
-      uint64_t pool_threads_env = 8192, max_nodes = 131072;
-      if (const char* e = getenv("MAPAD_POOL_THREADS")) pool_threads_env = strtoull(e, nullptr, 10);
-      if (const char* e = getenv("MAPAD_POOL_MAX_NODES")) max_nodes = strtoull(e, nullptr, 10);
-      const uint64_t hard_max = (uint64_t)MAPAD_POOL_MAX_NODE_CHUNKS << PoolWorkspace<WIDE>::NPC_SHIFT;
-      max_nodes = std::min<uint64_t>(max_nodes, hard_max);
-      // optional earlier stages with smaller caps (MAPAD_POOL_STAGES="8192,32768"): reads that outgrow a stage restart in
-      // the next one, packed densely, so that a stage's stragglers are at most cap / previous-cap times the typical read
-      uint64_t stage_caps[8];
-      int n_stages = 0;
-      if (const char* e = getenv("MAPAD_POOL_STAGES")) {
-        const char* q = e;
-        while (*q && n_stages < 7) {
-          char* end = nullptr;
-          const uint64_t v = strtoull(q, &end, 10);
-          if (end == q) break;
-          if (v >= 2 && v < max_nodes) stage_caps[n_stages++] = v;
-          q = *end == ',' ? end + 1 : end;
-        }
-      }
-      stage_caps[n_stages++] = max_nodes;
-      const uint64_t n_chunks = h->ws_budget / MAPAD_CHUNK_BYTES;
-      const int tblock = 128;
-      for (int stage = 0; stage < n_stages && n_work > 0; ++stage) {
-        const uint64_t stage_cap = stage_caps[stage];
-        uint64_t pool_threads = std::min<uint64_t>(pool_threads_env, n_chunks / 4);  // leave at least half of the pool for growth
-        pool_threads = std::min<uint64_t>(pool_threads, ((uint64_t)n_work + tblock - 1) / tblock * tblock);
-        pool_threads = pool_threads / tblock * tblock;
-        if (pool_threads < (uint64_t)tblock || stage_cap < 2) break;
-        CK(h->d_pool_next.reserve(n_chunks + 2));
-        CK(h->d_pool_tables.reserve(pool_threads * (MAPAD_POOL_MAX_NODE_CHUNKS + MAPAD_POOL_MAX_HEAP_CHUNKS)));
-        CK(h->d_pool_hits.reserve(pool_threads * MAPAD_MAX_HITS));
-        ChunkPool pool;
-        pool.base = h->d_ws.p;
-        pool.n_chunks = (uint32_t)n_chunks;
-        pool.next = h->d_pool_next.p + 2;
-        pool.head = reinterpret_cast<unsigned long long*>(h->d_pool_next.p);
-        k_pool_init<<<(unsigned)((n_chunks + 255) / 256), 256, 0, h->stream>>>(pool, (uint32_t)(2 * pool_threads));
-        ++launches;
-        CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));
-        if (trace_stats) { CK(h->d_lane_stats.reserve(2)); CK(cudaMemsetAsync(h->d_lane_stats.p, 0, 16, h->stream)); }
-        // tuning aid: MAPAD_POOL_SMEM_PAD=<bytes> of unused dynamic shared memory per block limits how many blocks share an
-        // SM (e.g. 110000 -> 2, 74000 -> 3) without touching the kernel; 0 = the register-limited 4 blocks per SM
-        static const size_t smem_pad = getenv("MAPAD_POOL_SMEM_PAD") ? (size_t)strtoull(getenv("MAPAD_POOL_SMEM_PAD"), nullptr, 10) : 0;
-        if (smem_pad) CK(cudaFuncSetAttribute(k_search_pool<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pad));
-        k_search_pool<WIDE><<<(unsigned)(pool_threads / tblock), tblock, smem_pad, h->stream>>>(
-            ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, pool, h->d_pool_tables.p, h->d_pool_hits.p, (uint32_t)stage_cap, work, n_work,
-            deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p, (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
-            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu), trace_stats ? h->d_lane_stats.p : nullptr, profile_iters);
-        ++launches;
-        CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        CK(cudaGetLastError());
-        if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the thread lane was cut short for profiling, no results"; return MAPAD_ELIMIT; }
-        const uint32_t n_def = h->h_cur.p->n_deferred;
-        trace("pool", n_work, n_def, stage_cap);
-        if (trace_stats) {
-          unsigned long long ls[2] = {0, 0};
-          CK(cudaMemcpyAsync(ls, h->d_lane_stats.p, 16, cudaMemcpyDeviceToHost, h->stream));
-          CK(cudaStreamSynchronize(h->stream));
-          fprintf(stderr, "[mapad trace] handle=%p pool lane utilisation %.3f (threads=%llu)\n", (void*)h, ls[1] ? (double)ls[0] / (double)ls[1] : 0.0,
-                  (unsigned long long)pool_threads);
-        }
-        work = deferred;
-        deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
-        n_work = n_def;
-        if (!cap_env) cap = std::max<uint64_t>(cap, stage_cap * 16);  // the warp lanes continue above the pool lane's limit
-      }
-    }
-    for (int lane = 0; n_work > 0; ++lane) {
-      if (cap > full_cap) cap = full_cap;
-      // 4 warps per block, 1408 heap entries per warp in shared memory, up to 4 blocks per SM.  (A one-warp-per-block shape
-      // with ~200 KB of heap on chip was measured and dropped: with many handles in flight its blocks monopolise SMs.)
-      const int warps_per_block = 4, block = warps_per_block * 32;
-      uint32_t hs = 1408;
-      if (hs_env) hs = (uint32_t)std::min<uint64_t>(3400, std::max<uint64_t>(8, strtoull(hs_env, nullptr, 10)));
-      const size_t smem = (size_t)warps_per_block * ((size_t)hs * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA);
-      // the attribute is per function, not per launch: always ask for the largest shape so that handles running in
-      // other host threads never lower it under a pending launch
-      CK(cudaFuncSetAttribute(k_search_warp<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(4 * (3400u * sizeof(HeapEnt) + MAPAD_WARP_SMEM_EXTRA))));
-      uint64_t warps_mem = h->ws_budget / (cap * per_entry);
-      uint64_t warps = std::min<uint64_t>(warps_mem, (uint64_t)h->n_sm * 16);
-      warps = std::min<uint64_t>(warps, ((uint64_t)n_work + warps_per_block - 1) / warps_per_block * warps_per_block);
-      int grid = (int)(warps / warps_per_block);
-      if (grid < 1) {
-        if (warps_mem < 1) { h->err = "search workspace does not fit the device memory budget"; return MAPAD_ELIMIT; }
-        grid = 1;
-      }
-      const uint64_t n_wslots = (uint64_t)grid * warps_per_block;
-      const size_t heap_bytes = (size_t)n_wslots * cap * sizeof(HeapEnt);
-      const size_t node_bytes = (size_t)n_wslots * cap * sizeof(NodeT<WIDE>);
-      CK(h->d_ws.reserve(heap_bytes + node_bytes + 256, true));
-      HeapEnt* heap_base = reinterpret_cast<HeapEnt*>(h->d_ws.p);
-      NodeT<WIDE>* node_base = reinterpret_cast<NodeT<WIDE>*>(h->d_ws.p + ((heap_bytes + 63) & ~(size_t)63));
-      CK(cudaMemsetAsync(h->d_cur.p, 0, 2 * sizeof(uint32_t), h->stream));  // queue head + deferred counter
-      k_search_warp<WIDE><<<grid, block, smem, h->stream>>>(ix, P, rb, h->d_bound.p, h->d_delta.p, h->d_dcomp.p, heap_base, node_base,
-                                                            (uint32_t)cap, hs, work, n_work, deferred, h->d_cur.p, h->d_mid.p, h->d_hits.p,
-                                                            (uint32_t)std::min<size_t>(h->d_hits.cap, 0xffffffffu), h->d_ops.p,
-                                                            (uint32_t)std::min<size_t>(h->d_ops.cap, 0xffffffffu));
-      ++launches;
-      CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      CK(cudaGetLastError());
-      const uint32_t n_def = h->h_cur.p->n_deferred;
-      trace("warp", n_work, n_def, cap);
-      if (n_def == 0) break;
-      if (cap >= full_cap) { h->err = "read exceeded the full-size search workspace"; return MAPAD_ELIMIT; }
-      work = deferred;
-      deferred = deferred == h->d_deferred_a.p ? h->d_deferred_b.p : h->d_deferred_a.p;
-      n_work = n_def;
-      cap *= 16;
-    }
     }
     CK(cudaEventRecord(h->ev[3], h->stream));
     // K2 bump-allocates hits and edit operations; when a cursor overshot its pool the batch is re-run with larger pools

@@ -214,18 +214,9 @@ struct HitTmp {  // HitInterval before its edit operations are extracted
 #define MAPAD_MAX_HITS 20   // the search returns once len() > 9, one expansion adds at most 9 (mapping.rs:1348)
 #define MAPAD_NO_NODE 0xffffffffu
 
-// Optional per-step statistics for the host-side SIMT model (tools/simt_model.cpp); compiled out everywhere else.
-#if defined(MAPAD_STEP_STATS) && !defined(__CUDA_ARCH__)
-struct StepStats { int trickle, n_cand, pushes, bubble[9]; int n_heap_idx; uint32_t heap_idx[512]; };
-extern thread_local StepStats* g_step_stats;
-#define MAPAD_STAT(x) do { if (g_step_stats) { x; } } while (0)
-#else
-#define MAPAD_STAT(x) do { } while (0)
-#endif
-
 // Workspace policies.  A workspace provides: node(id) -> NodeT&, ensure_node(id) / ensure_heap(n) (grow or
-// refuse), heap() -> a store with get/set, and the hit array.  `Workspace` is the contiguous per-thread /
-// per-warp arena; PoolWorkspace (search_pool.cuh) grows in fixed-size chunks taken from a shared pool.
+// refuse), heap() -> a store with get/set, and the hit array.  `Workspace` is the contiguous arena of the sequential
+// reference loop (emulation tests); GroupWorkspace (search_group.cuh) grows in chunks taken from the device-wide pool.
 template <bool WIDE>
 struct PlainNodes {
   NodeT<WIDE>* p;
@@ -243,8 +234,8 @@ struct Workspace {  // one per persistent thread; lives in global memory
   MAPAD_DEV uint32_t min_cap() const { return cap; }
   struct Store {
     HeapEnt* d;
-    MAPAD_DEV HeapEnt get(uint32_t i) const { MAPAD_STAT(if (g_step_stats->n_heap_idx < 512) g_step_stats->heap_idx[g_step_stats->n_heap_idx++] = i); return d[i]; }
-    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { MAPAD_STAT(if (g_step_stats->n_heap_idx < 512) g_step_stats->heap_idx[g_step_stats->n_heap_idx++] = i); d[i] = e; }
+    MAPAD_DEV HeapEnt get(uint32_t i) const { return d[i]; }
+    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { d[i] = e; }
   };
   MAPAD_DEV Store heap() const { return Store{heap_}; }
 };
@@ -348,7 +339,6 @@ MAPAD_DEV void mm_push(const H& d, uint32_t& n, HeapEnt e) {
     climb_max = !min_level;
   }
   while (i >= 3) {
-    MAPAD_STAT(g_step_stats->bubble[g_step_stats->pushes > 0 ? g_step_stats->pushes - 1 : 0] += 1);
     uint32_t gp = (((i - 1) >> 1) - 1) >> 1;
     HeapEnt ge = d.get(gp);
     if (climb_max ? (e.score > ge.score) : (e.score < ge.score)) { d.set(i, ge); i = gp; } else break;
@@ -361,7 +351,6 @@ MAPAD_DEV void mm_trickle_down(const H& d, uint32_t n, uint32_t i) {
   while (true) {
     const uint32_t c1 = 2 * i + 1;
     if (c1 >= n) break;
-    MAPAD_STAT(g_step_stats->trickle += 1);
     const uint32_t g1 = 4 * i + 3;
     // the six candidates (2 children, 4 grandchildren) are fetched independently of each other so that a
     // level living in HBM costs one memory latency; candidate indices are increasing, so "stop at the first
@@ -513,7 +502,6 @@ MAPAD_DEV void check_and_push(WS& ws, SearchState<WIDE>& st, Frame f, uint32_t p
     return;
   }
   if (!ws.ensure_heap(st.heap_n)) { st.overflow = true; return; }
-  MAPAD_STAT(if (g_step_stats->pushes < 9) g_step_stats->pushes += 1);
   mm_push(ws.heap(), st.heap_n, HeapEnt{f.score, id});
 }
 
@@ -617,7 +605,6 @@ MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJo
     const float mm_score = fadd(row.d[pen_idx], sf.score);
     if (!bound_reject(bc, fadd(mm_score, lower_bound))) { codes |= (uint64_t)(8 | k) << (4 * n_cand); n_cand += 1; }
   }
-  MAPAD_STAT(g_step_stats->n_cand = n_cand);
   for (int i = 0; i < n_cand && !st.overflow; ++i) {
     const uint32_t code = (uint32_t)(codes >> (4 * i)) & 15u;
     const uint32_t type = code >> 2, k = code & 3u;
@@ -710,7 +697,6 @@ MAPAD_DEV int search_step(const DevIndex& ix, const DevParams& P, const SearchJo
       n_cand += 1;
     }
   }
-  MAPAD_STAT(g_step_stats->n_cand = n_cand);
   for (int i = 0; i < n_cand && !st.overflow; ++i) check_and_push<WIDE, WS>(ws, st, cand[i], sf.node, cand_op[i], L, bc, P);
 #endif
   if (st.overflow) return STEP_OVERFLOW;

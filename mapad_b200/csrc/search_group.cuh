@@ -71,6 +71,19 @@ MAPAD_DEV void gpool_release(const GChunkPool& p, uint32_t idx) {
 #endif
 }
 
+// Back-off while waiting for the pool (device: __nanosleep; emulation: let the other groups run).
+#if !defined(__CUDA_ARCH__)
+extern "C" void mapad_simt_emu_yield(void);
+#endif
+template <int G>
+MAPAD_DEV void dev_backoff() {
+#if defined(__CUDA_ARCH__)
+  __nanosleep(2000);
+#else
+  if (G > 1) mapad_simt_emu_yield();
+#endif
+}
+
 // ---- family layout of the min-max heap ----------------------------------------------------------
 // 1-based position x -> (line, slot).  Positions 1..3 live in line 0 (slots 0..2).  A position on an even level >= 2
 // is a CHILD of its owner x >> 1 (slots 0, 1), one on an odd level >= 3 a GRANDCHILD of its owner x >> 2 (slots 2..5).
@@ -137,6 +150,7 @@ struct GroupWorkspace {
   HeapEnt* top;          // shared memory: TOPL lines of 8 entries
   HitTmp* hits;
   uint32_t max_nodes, max_heap;
+  uint32_t patience;     // how long (in 2 us back-off rounds) this group waits for a chunk when the pool is dry
   int gl;                // lane in group
 
   MAPAD_DEV Node& node(uint32_t id) const {
@@ -155,9 +169,18 @@ struct GroupWorkspace {
     const HLoc l = heap_loc(i0 + 1u);
     return line_ptr(l.line) + l.slot;
   }
+  // The pool is shared by every group of every launch on the device.  When it is dry the group waits for chunks that
+  // finishing reads give back — the longer, the more work its own read has already absorbed (patience is set by the caller
+  // in proportion to the frames popped so far), so that young reads step aside first (they are handed back and re-run).
   MAPAD_DEV uint32_t acquire_chunk() const {
     uint32_t got = MAPAD_GPOOL_EMPTY;
-    if (gl == 0) got = gpool_acquire(pool);
+    if (gl == 0) {
+      got = gpool_acquire(pool);
+      for (uint32_t w = 0; got == MAPAD_GPOOL_EMPTY && w < patience; ++w) {
+        dev_backoff<G>();
+        got = gpool_acquire(pool);
+      }
+    }
     return Grp<G>::shfl(got, 0);
   }
   MAPAD_DEV bool ensure_node(uint32_t id) {
@@ -185,6 +208,9 @@ struct GroupWorkspace {
     return true;
   }
   MAPAD_DEV uint32_t min_cap() const { return max_nodes; }
+  MAPAD_DEV void release_base() const {  // group exit: the two base chunks go back to the pool
+    if (gl == 0) { gpool_release(pool, table[0]); gpool_release(pool, table[nt]); }
+  }
   MAPAD_DEV void release_extra() {  // keep chunk 0 of each kind
     if (gl == 0) {
       for (uint32_t c = n_node_chunks; c > 1; --c) gpool_release(pool, table[c - 1]);
@@ -226,7 +252,10 @@ struct GroupLaunch {
   uint32_t op_cap;
   uint32_t iter_budget;    // profiling aid: stop every group after this many expansions (0 = off)
   uint32_t flags_or;       // ORed into ReadMid::flags (bit 1: the read went through a retry launch)
+  uint32_t patient;        // 1: never hand a read back, wait for the pool (last-resort launches)
 };
+#define MAPAD_POOL_TIMEOUT_FLAG 4u   // Cursors::overflow bit: a group found no base chunks within the start-up patience
+#define MAPAD_PATIENCE_MAX 10000000u // back-off rounds of 2 us: 20 s
 
 // ---------------------------------------------------------------------------------------------
 // One read's search, executed by the G lanes of a group.  Memory discipline: the sequential state that lives in
@@ -619,12 +648,23 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
   ws.nt = a.nt; ws.ht = a.ht;
   ws.table = a.tables + (size_t)slot * (a.nt + a.ht);
   ws.gl = gl;
-  // group `slot` owns chunks 2 slot (nodes) and 2 slot + 1 (heap) for good; chunks >= 2 n_groups are pooled
-  if (gl == 0) { ws.table[0] = 2 * slot; ws.table[a.nt] = 2 * slot + 1; }
+  // every group takes its two base chunks (nodes, heap) from the device-wide pool when it starts and returns them when it exits
+  ws.patience = MAPAD_PATIENCE_MAX;
+  const uint32_t c_nodes = ws.acquire_chunk();
+  const uint32_t c_heap = c_nodes != MAPAD_GPOOL_EMPTY ? ws.acquire_chunk() : MAPAD_GPOOL_EMPTY;
+  if (c_heap == MAPAD_GPOOL_EMPTY) {
+    if (gl == 0) {
+      if (c_nodes != MAPAD_GPOOL_EMPTY) gpool_release(a.pool, c_nodes);
+      dev_atomic_or(&a.cur->overflow, MAPAD_POOL_TIMEOUT_FLAG);
+    }
+    return;
+  }
+  if (gl == 0) { ws.table[0] = c_nodes; ws.table[a.nt] = c_heap; }
+  Grp<G>::sync();
   ws.n_node_chunks = 1;
   ws.n_heap_chunks = 1;
-  ws.node0 = reinterpret_cast<typename GS::Node*>(a.pool.base + ((size_t)(2 * slot) << MAPAD_GCHUNK_SHIFT));
-  ws.heap0 = reinterpret_cast<HeapEnt*>(a.pool.base + ((size_t)(2 * slot + 1) << MAPAD_GCHUNK_SHIFT));
+  ws.node0 = reinterpret_cast<typename GS::Node*>(a.pool.base + ((size_t)c_nodes << MAPAD_GCHUNK_SHIFT));
+  ws.heap0 = reinterpret_cast<HeapEnt*>(a.pool.base + ((size_t)c_heap << MAPAD_GCHUNK_SHIFT));
   ws.top = smem_top;
   ws.hits = a.hit_base + (size_t)slot * MAPAD_MAX_HITS;
   ws.max_nodes = a.max_nodes;
@@ -656,9 +696,16 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
       gs.begin(a.ix, split);
       have = true;
     }
+    {  // patience grows with the work already invested in this read (2 us per popped frame, at least 0.4 ms)
+      const uint32_t p = gs.frames < 200u ? 200u : gs.frames;
+      ws.patience = a.patient ? MAPAD_PATIENCE_MAX : (p < MAPAD_PATIENCE_MAX ? p : MAPAD_PATIENCE_MAX);
+#if !defined(__CUDA_ARCH__)
+      if (G == 1) ws.patience = 0;  // the emulation runs per-thread groups one after the other: nobody to wait for
+#endif
+    }
     const int rc = gs.step(a.ix, a.P, job);
     busy_iters += 1;
-    if (a.iter_budget && busy_iters >= a.iter_budget) break;
+    if (a.iter_budget && busy_iters >= a.iter_budget) { ws.release_extra(); break; }
     if (rc == STEP_CONTINUE) continue;
     have = false;
     Grp<G>::sync();
@@ -701,6 +748,8 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
     Grp<G>::sync();  // the tree is no longer read: its chunks may go back to the pool
     ws.release_extra();
   }
+  Grp<G>::sync();
+  ws.release_base();
 }
 
 #if defined(__CUDACC__)

@@ -164,10 +164,10 @@ int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, co
   // launch state
   const int ng = go.n_groups;
   const uint32_t n_chunks = go.pool_chunks;
-  if (n_chunks < 2u * (uint32_t)ng) return MAPAD_EINVAL;
+  if (n_chunks < 4u) return MAPAD_EINVAL;
   std::vector<uint8_t> pool_mem((size_t)n_chunks * MAPAD_GCHUNK_BYTES + 64);
   std::vector<uint32_t> pool_next(n_chunks + 2);
-  unsigned long long pool_head = 2u * (uint32_t)ng < n_chunks ? 2u * (uint32_t)ng : MAPAD_GPOOL_EMPTY;
+  unsigned long long pool_head = 0;  // every chunk is free; groups take their base chunks themselves
   for (uint32_t i = 0; i < n_chunks; ++i) pool_next[i] = i + 1 < n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
   GroupLaunch<WIDE> a;
   a.ix = ix; a.P = P; a.rb = rb; a.bound_table = bp.bound_table.data(); a.delta = delta.data(); a.dcomp = dcomp.data();
@@ -201,9 +201,10 @@ int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, co
   std::vector<uint32_t> work2;
   for (int attempt = 0;; ++attempt) {
     cur.queue_head = 0; cur.n_deferred = 0;
-    pool_head = 2u * (uint32_t)groups_now < n_chunks ? 2u * (uint32_t)groups_now : MAPAD_GPOOL_EMPTY;
+    pool_head = 0;
     for (uint32_t i = 0; i < n_chunks; ++i) pool_next[i] = i + 1 < n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
     a.flags_or = attempt ? 2u : 0u;
+    a.patient = 0;
     switch (go.group_size) {
       case 1: launch_groups<WIDE, 1>(a, groups_now); break;
       case 2: launch_groups<WIDE, 2>(a, groups_now); break;
@@ -213,6 +214,7 @@ int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, co
       case 32: launch_groups<WIDE, 32>(a, groups_now); break;
       default: return MAPAD_EINVAL;
     }
+    if (cur.overflow & MAPAD_POOL_TIMEOUT_FLAG) return MAPAD_ELIMIT;
     if (cur.n_deferred == 0) break;
     total_deferred += cur.n_deferred;
     if (groups_now == 1 && cur.n_deferred >= a.n_work) { if (n_deferred_out) *n_deferred_out = total_deferred; return MAPAD_ELIMIT; }

@@ -174,6 +174,10 @@ uint32_t mapad_simt_emu_ballot(int pred, int group_size) {
   return r;
 }
 
+void mapad_simt_emu_yield(void) {
+  if (g_sched) yield_to_main();
+}
+
 void mapad_simt_emu_sync(int group_size) {
   Sched* s = g_sched;
   LaneCtx& me = s->lanes[s->current];
