@@ -258,14 +258,15 @@ def main():
     t0 = time.time()
     free_b0, _ = torch.cuda.mem_get_info()
     inflight = max(1, min(len(timed_ids), int(os.environ.get("MAPAD_BENCH_INFLIGHT", "32"))))
+    # search workspace: ONE chunk pool per GPU shared by all handles (75 % of the memory left after the index, sized by the
+    # library when the first handle is created; MAPAD_WS_BYTES overrides)
+    api.plan_handles(local_rank, inflight + 1)
     if world == 1:
-        os.environ["MAPAD_WS_BYTES"] = str(64 << 20)  # the first handle only carries the index; the working handles are sized below
         mapper = api.Mapper(index, params, device=local_rank)
         meta, blob_ptr, nbytes = mapper.export_index()
         keep_blob = mapper
     else:
         # index replicated per GPU: built + re-laid-out on rank 0, ONE NCCL broadcast of the device blob over NVLink
-        os.environ["MAPAD_WS_BYTES"] = str(64 << 20)
         if rank == 0:
             mapper0 = api.Mapper(index, params, device=local_rank)
             meta, _, nbytes = mapper0.export_index()
@@ -297,8 +298,6 @@ def main():
     # Chunks are pipelined: `inflight` handles share the index blob, each owns a stream and a workspace, so the straggler reads
     # of one chunk (per-read work is heavy-tailed over four orders of magnitude) overlap with the next chunks.  The timed region
     # spans from the first launch to the completion of the last chunk.
-    free_b, _total_b = torch.cuda.mem_get_info()
-    os.environ["MAPAD_WS_BYTES"] = str(int(min(free_b * 0.8 / inflight, 48 << 30)))  # search workspace budget per handle
     mappers = [api.Mapper.from_device_blob(meta, blob_ptr, nbytes, index, params, device=local_rank) for _ in range(inflight)]
     streams = [torch.cuda.Stream() for _ in mappers]
     for mp, st in zip(mappers, streams):

@@ -266,9 +266,10 @@ int mapad_gpu_create_from_device_blob(const void* meta, void* dev_ptr, uint64_t 
  * (/root/reference/src/distributed/worker.rs:45-215) for single-box runs; the caller shards each chunk of reads over the
  * handles and merges the results in input order like the dispatcher (src/distributed/dispatcher.rs:341-379). */
 int mapad_gpu_clone_to_device(mapad_gpu* src, int device, mapad_gpu** out);
-/* Announces how many handles the caller is about to create on `device`: each then sizes its search workspace (the chunk
- * pool the per-read heaps / edit trees grow in — the thread-local scratch of mapping.rs:146-149) to an equal share of the
- * free device memory instead of the single-handle default.  MAPAD_WS_BYTES overrides both. */
+/* Announces how many handles the caller is about to create on `device`.  All handles of a device share ONE search
+ * workspace (the chunk pool the per-read heaps / edit trees grow in — the thread-local scratch of mapping.rs:146-149),
+ * allocated with the first handle: 75 % of the free device memory, but leaving 1 GiB per announced handle for their batch
+ * buffers.  MAPAD_WS_BYTES overrides the size. */
 int mapad_gpu_plan_handles(int device, int n_handles);
 int mapad_gpu_set_params(mapad_gpu* h, const mapad_params* params);
 int mapad_gpu_map_batch(mapad_gpu* h, const mapad_reads* in, uint32_t flags, mapad_results* out);

@@ -176,7 +176,8 @@ struct PinBuf {  // grow-only pinned host buffer
 namespace {
 struct DeviceArena {
   uint8_t* base = nullptr;
-  uint32_t* next = nullptr;   // [0..1]: Treiber head (64 bit), [2..]: next pointers
+  uint32_t* next = nullptr;   // next pointers of the free stacks
+  unsigned long long* heads = nullptr;  // MAPAD_GPOOL_SHARDS Treiber heads, 128 bytes apart
   uint64_t n_chunks = 0;
   int refs = 0;
 };
@@ -262,7 +263,7 @@ static int init_handle(mapad_gpu* h, int device) {
 }
 
 // The search workspace (chunk pool) is allocated after the first index blob of the device.  Size: MAPAD_WS_BYTES, else 75 %
-// of the free device memory minus 0.5 GiB per handle announced with mapad_gpu_plan_handles (their batch buffers).
+// of the free device memory, leaving at least 1 GiB per handle announced with mapad_gpu_plan_handles (their batch buffers).
 static int g_planned_handles[64] = {0};  // per device
 static int alloc_workspace(mapad_gpu* h) {
   std::lock_guard<std::mutex> lock(g_arena_mu);
@@ -273,7 +274,7 @@ static int alloc_workspace(mapad_gpu* h) {
     const char* env = getenv("MAPAD_WS_BYTES");
     size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : (size_t)(free_b * 0.75);
     if (!env) {
-      const size_t reserve = (size_t)g_planned_handles[h->device & 63] << 29;
+      const size_t reserve = (size_t)g_planned_handles[h->device & 63] << 30;
       if (budget + reserve > (size_t)(free_b * 0.9)) budget = (size_t)(free_b * 0.9) > reserve ? (size_t)(free_b * 0.9) - reserve : 0;
     }
     budget = std::max<size_t>(budget, (size_t)64 << 20);
@@ -284,11 +285,14 @@ static int alloc_workspace(mapad_gpu* h) {
     uint64_t n_chunks = budget >> MAPAD_GCHUNK_SHIFT;
     if (const char* e = getenv("MAPAD_TEST_POOL_CHUNKS")) n_chunks = std::min<uint64_t>(n_chunks, strtoull(e, nullptr, 10));  // test hook: tiny pool
     CK(cudaMalloc(&ar.base, (n_chunks << MAPAD_GCHUNK_SHIFT) + 4096));
-    if (cudaMalloc(&ar.next, (n_chunks + 2) * sizeof(uint32_t)) != cudaSuccess) { cudaFree(ar.base); ar.base = nullptr; h->err = "cudaMalloc(pool links)"; return MAPAD_ENOMEM; }
+    if (cudaMalloc(&ar.next, (n_chunks + 2) * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ar.heads, (size_t)MAPAD_GPOOL_SHARDS * MAPAD_GPOOL_HEAD_STRIDE * sizeof(unsigned long long)) != cudaSuccess) {
+      cudaFree(ar.base); cudaFree(ar.next); ar.base = nullptr; ar.next = nullptr; h->err = "cudaMalloc(pool links)"; return MAPAD_ENOMEM;
+    }
     ar.n_chunks = n_chunks;
     GChunkPool pool;
-    pool.base = ar.base; pool.n_chunks = (uint32_t)n_chunks; pool.next = ar.next + 2; pool.head = reinterpret_cast<unsigned long long*>(ar.next);
-    k_gpool_init<<<(unsigned)((n_chunks + 255) / 256), 256>>>(pool, 0u);
+    pool.base = ar.base; pool.n_chunks = (uint32_t)n_chunks; pool.next = ar.next; pool.heads = ar.heads;
+    k_gpool_init<<<(unsigned)((std::max<uint64_t>(n_chunks, MAPAD_GPOOL_SHARDS) + 255) / 256), 256>>>(pool);
     CK(cudaDeviceSynchronize());
   }
   ar.refs += 1;
@@ -302,8 +306,8 @@ static void release_workspace(mapad_gpu* h) {
   DeviceArena& ar = *h->arena;
   h->arena = nullptr;
   if (--ar.refs == 0) {
-    cudaFree(ar.base); cudaFree(ar.next);
-    ar.base = nullptr; ar.next = nullptr; ar.n_chunks = 0;
+    cudaFree(ar.base); cudaFree(ar.next); cudaFree(ar.heads);
+    ar.base = nullptr; ar.next = nullptr; ar.heads = nullptr; ar.n_chunks = 0;
   }
 }
 
@@ -571,8 +575,8 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
     CK(h->d_pool_hits.reserve(use * MAPAD_MAX_HITS));
     a.pool.base = ar.base;
     a.pool.n_chunks = (uint32_t)n_chunks;
-    a.pool.next = ar.next + 2;
-    a.pool.head = reinterpret_cast<unsigned long long*>(ar.next);
+    a.pool.next = ar.next;
+    a.pool.heads = ar.heads;
     a.tables = h->d_pool_tables.p;
     a.hit_base = h->d_pool_hits.p;
     a.cur = h->d_cur.p; a.mid = h->d_mid.p;

@@ -27,48 +27,67 @@ namespace mapad {
 #define MAPAD_GCHUNK_BYTES (1u << MAPAD_GCHUNK_SHIFT)
 #define MAPAD_GPOOL_EMPTY 0xffffffffu
 
-// Treiber stack of free chunk ids; the 32-bit tag in the upper half of `head` defeats ABA.
+// Free chunk ids live in MAPAD_GPOOL_SHARDS independent Treiber stacks (heads 128 bytes apart; the 32-bit tag in the upper
+// half of a head defeats ABA).  A group works on the shard its slot number selects and scans the others only when that one
+// is empty, so that the thousands of groups of all launches in flight do not hammer one atomic (measured: with a single
+// stack the compare-and-swap loop accounted for 37 % of the stall samples of a saturated launch, profiles/r2_*).
+#define MAPAD_GPOOL_SHARDS 256u
+#define MAPAD_GPOOL_HEAD_STRIDE 16u  // in 8-byte words
 struct GChunkPool {
   uint8_t* base;
   uint32_t n_chunks;
-  unsigned long long* head;
+  unsigned long long* heads;  // MAPAD_GPOOL_SHARDS x MAPAD_GPOOL_HEAD_STRIDE words
   uint32_t* next;
 };
 
-MAPAD_DEV uint32_t gpool_acquire(const GChunkPool& p) {
+MAPAD_DEV uint32_t gpool_pop(const GChunkPool& p, uint32_t shard) {
+  unsigned long long* head = p.heads + (size_t)shard * MAPAD_GPOOL_HEAD_STRIDE;
 #if defined(__CUDA_ARCH__)
-  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p.head);
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(head);
   while (true) {
     const uint32_t idx = (uint32_t)old;
     if (idx == MAPAD_GPOOL_EMPTY) return idx;
     const uint32_t nxt = reinterpret_cast<volatile uint32_t*>(p.next)[idx];
     const unsigned long long neu = (((old >> 32) + 1ull) << 32) | nxt;
-    const unsigned long long seen = atomicCAS(p.head, old, neu);
+    const unsigned long long seen = atomicCAS(head, old, neu);
     if (seen == old) return idx;
     old = seen;
   }
 #else
-  const uint32_t idx = (uint32_t)*p.head;
+  const uint32_t idx = (uint32_t)*head;
   if (idx == MAPAD_GPOOL_EMPTY) return idx;
-  *p.head = p.next[idx];
+  *head = p.next[idx];
   return idx;
 #endif
 }
-MAPAD_DEV void gpool_release(const GChunkPool& p, uint32_t idx) {
+MAPAD_DEV uint32_t gpool_acquire(const GChunkPool& p, uint32_t hint) {
+  for (uint32_t k = 0; k < MAPAD_GPOOL_SHARDS; ++k) {
+    const uint32_t got = gpool_pop(p, (hint + k) & (MAPAD_GPOOL_SHARDS - 1u));
+    if (got != MAPAD_GPOOL_EMPTY) return got;
+  }
+  return MAPAD_GPOOL_EMPTY;
+}
+MAPAD_DEV void gpool_release(const GChunkPool& p, uint32_t idx, uint32_t hint) {
+  unsigned long long* head = p.heads + (size_t)(hint & (MAPAD_GPOOL_SHARDS - 1u)) * MAPAD_GPOOL_HEAD_STRIDE;
 #if defined(__CUDA_ARCH__)
-  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(p.head);
+  unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(head);
   while (true) {
     reinterpret_cast<volatile uint32_t*>(p.next)[idx] = (uint32_t)old;
     __threadfence();
     const unsigned long long neu = (((old >> 32) + 1ull) << 32) | idx;
-    const unsigned long long seen = atomicCAS(p.head, old, neu);
+    const unsigned long long seen = atomicCAS(head, old, neu);
     if (seen == old) return;
     old = seen;
   }
 #else
-  p.next[idx] = (uint32_t)*p.head;
-  *p.head = idx;
+  p.next[idx] = (uint32_t)*head;
+  *head = idx;
 #endif
+}
+// host-side helper shared with the emulation harness: chunk i starts in shard i % SHARDS
+inline void gpool_init_host(uint32_t n_chunks, unsigned long long* heads, uint32_t* next) {
+  for (uint32_t s = 0; s < MAPAD_GPOOL_SHARDS; ++s) heads[(size_t)s * MAPAD_GPOOL_HEAD_STRIDE] = s < n_chunks ? s : MAPAD_GPOOL_EMPTY;
+  for (uint32_t i = 0; i < n_chunks; ++i) next[i] = i + MAPAD_GPOOL_SHARDS < n_chunks ? i + MAPAD_GPOOL_SHARDS : MAPAD_GPOOL_EMPTY;
 }
 
 // Back-off while waiting for the pool (device: __nanosleep; emulation: let the other groups run).
@@ -151,6 +170,7 @@ struct GroupWorkspace {
   HitTmp* hits;
   uint32_t max_nodes, max_heap;
   uint32_t patience;     // how long (in 2 us back-off rounds) this group waits for a chunk when the pool is dry
+  uint32_t shard;        // this group's home shard of the pool
   int gl;                // lane in group
 
   MAPAD_DEV Node& node(uint32_t id) const {
@@ -175,10 +195,10 @@ struct GroupWorkspace {
   MAPAD_DEV uint32_t acquire_chunk() const {
     uint32_t got = MAPAD_GPOOL_EMPTY;
     if (gl == 0) {
-      got = gpool_acquire(pool);
+      got = gpool_acquire(pool, shard);
       for (uint32_t w = 0; got == MAPAD_GPOOL_EMPTY && w < patience; ++w) {
         dev_backoff<G>();
-        got = gpool_acquire(pool);
+        got = gpool_acquire(pool, shard);
       }
     }
     return Grp<G>::shfl(got, 0);
@@ -209,12 +229,12 @@ struct GroupWorkspace {
   }
   MAPAD_DEV uint32_t min_cap() const { return max_nodes; }
   MAPAD_DEV void release_base() const {  // group exit: the two base chunks go back to the pool
-    if (gl == 0) { gpool_release(pool, table[0]); gpool_release(pool, table[nt]); }
+    if (gl == 0) { gpool_release(pool, table[0], shard); gpool_release(pool, table[nt], shard); }
   }
   MAPAD_DEV void release_extra() {  // keep chunk 0 of each kind
     if (gl == 0) {
-      for (uint32_t c = n_node_chunks; c > 1; --c) gpool_release(pool, table[c - 1]);
-      for (uint32_t c = n_heap_chunks; c > 1; --c) gpool_release(pool, table[nt + c - 1]);
+      for (uint32_t c = n_node_chunks; c > 1; --c) gpool_release(pool, table[c - 1], shard);
+      for (uint32_t c = n_heap_chunks; c > 1; --c) gpool_release(pool, table[nt + c - 1], shard);
     }
     n_node_chunks = 1;
     n_heap_chunks = 1;
@@ -650,11 +670,12 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
   ws.gl = gl;
   // every group takes its two base chunks (nodes, heap) from the device-wide pool when it starts and returns them when it exits
   ws.patience = MAPAD_PATIENCE_MAX;
+  ws.shard = (slot * 2654435761u) >> 24;  // spread neighbouring groups (and the launches in flight) over the 256 shards
   const uint32_t c_nodes = ws.acquire_chunk();
   const uint32_t c_heap = c_nodes != MAPAD_GPOOL_EMPTY ? ws.acquire_chunk() : MAPAD_GPOOL_EMPTY;
   if (c_heap == MAPAD_GPOOL_EMPTY) {
     if (gl == 0) {
-      if (c_nodes != MAPAD_GPOOL_EMPTY) gpool_release(a.pool, c_nodes);
+      if (c_nodes != MAPAD_GPOOL_EMPTY) gpool_release(a.pool, c_nodes, ws.shard);
       dev_atomic_or(&a.cur->overflow, MAPAD_POOL_TIMEOUT_FLAG);
     }
     return;
@@ -765,10 +786,10 @@ __global__ void __launch_bounds__(MAPAD_GROUP_BLOCK) k_search_group(const __grid
   group_search_lane<WIDE, G, TOPL>(a, slot, (int)(threadIdx.x % G), top);
 }
 
-__global__ void k_gpool_init(GChunkPool p, uint32_t first_free) {
+__global__ void k_gpool_init(GChunkPool p) {  // chunk i starts in shard i % SHARDS
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < p.n_chunks) p.next[i] = i + 1 < p.n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
-  if (i == 0) *p.head = first_free < p.n_chunks ? (unsigned long long)first_free : (unsigned long long)MAPAD_GPOOL_EMPTY;
+  if (i < p.n_chunks) p.next[i] = i + MAPAD_GPOOL_SHARDS < p.n_chunks ? i + MAPAD_GPOOL_SHARDS : MAPAD_GPOOL_EMPTY;
+  if (i < MAPAD_GPOOL_SHARDS) p.heads[(size_t)i * MAPAD_GPOOL_HEAD_STRIDE] = i < p.n_chunks ? (unsigned long long)i : (unsigned long long)MAPAD_GPOOL_EMPTY;
 }
 #endif
 

@@ -167,12 +167,12 @@ int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, co
   if (n_chunks < 4u) return MAPAD_EINVAL;
   std::vector<uint8_t> pool_mem((size_t)n_chunks * MAPAD_GCHUNK_BYTES + 64);
   std::vector<uint32_t> pool_next(n_chunks + 2);
-  unsigned long long pool_head = 0;  // every chunk is free; groups take their base chunks themselves
-  for (uint32_t i = 0; i < n_chunks; ++i) pool_next[i] = i + 1 < n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
+  std::vector<unsigned long long> pool_heads((size_t)MAPAD_GPOOL_SHARDS * MAPAD_GPOOL_HEAD_STRIDE);
+  gpool_init_host(n_chunks, pool_heads.data(), pool_next.data());  // every chunk is free; groups take their base chunks themselves
   GroupLaunch<WIDE> a;
   a.ix = ix; a.P = P; a.rb = rb; a.bound_table = bp.bound_table.data(); a.delta = delta.data(); a.dcomp = dcomp.data();
   a.pool.base = (uint8_t*)(((uintptr_t)pool_mem.data() + 63) & ~(uintptr_t)63);
-  a.pool.n_chunks = n_chunks; a.pool.head = &pool_head; a.pool.next = pool_next.data();
+  a.pool.n_chunks = n_chunks; a.pool.heads = pool_heads.data(); a.pool.next = pool_next.data();
   a.max_nodes = P.edit_tree_limit + 64; a.max_heap = P.stack_limit + 64;
   a.nt = (a.max_nodes >> (MAPAD_GCHUNK_SHIFT - 5)) + 1;
   a.ht = (heap_lines_for(a.max_heap) >> (MAPAD_GCHUNK_SHIFT - 6)) + 1;
@@ -201,8 +201,7 @@ int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, co
   std::vector<uint32_t> work2;
   for (int attempt = 0;; ++attempt) {
     cur.queue_head = 0; cur.n_deferred = 0;
-    pool_head = 0;
-    for (uint32_t i = 0; i < n_chunks; ++i) pool_next[i] = i + 1 < n_chunks ? i + 1 : MAPAD_GPOOL_EMPTY;
+    gpool_init_host(n_chunks, pool_heads.data(), pool_next.data());
     a.flags_or = attempt ? 2u : 0u;
     a.patient = 0;
     switch (go.group_size) {
