@@ -453,8 +453,10 @@ MAPAD_DEV BoundCtx bound_ctx(const DevParams& P, const float* bound_table, int L
   else b.thr = P.test_threshold;
   return b;
 }
+// out of line on purpose: inlined, the compiler evaluates the division speculatively on every call of bound_reject
+MAPAD_DEV_NOINLINE bool bound_reject_continuous(float value, float scale, float cutoff) { return fdiv_rn(value, scale) < cutoff; }
 MAPAD_DEV bool bound_reject(const BoundCtx& b, float value) {
-  if (b.kind == BOUND_CONTINUOUS) return fdiv_rn(value, b.scale) < b.cutoff;
+  if (b.kind == BOUND_CONTINUOUS) return bound_reject_continuous(value, b.scale, b.cutoff);
   return value < b.thr;
 }
 MAPAD_DEV bool bound_reject_iterative(const BoundCtx& b, float value, float reference) {

@@ -277,6 +277,103 @@ struct GroupLaunch {
 #define MAPAD_POOL_TIMEOUT_FLAG 4u   // Cursors::overflow bit: a group found no base chunks within the start-up patience
 #define MAPAD_PATIENCE_MAX 10000000u // back-off rounds of 2 us: 20 s
 
+// FmdExtIterator for a lane group (dev_index.cuh::extend_all, fmd_index.rs:117-182): the two occ blocks hold 8 (narrow) or
+// 16 (wide) words of 2-bit codes; with G >= 8 lanes 0..3 of every 8 count the words of the block of row lower - 1, lanes
+// 4..7 those of the block of row lower + size - 1, and three xor-shuffles give every lane both totals.
+template <bool WIDE, int G>
+MAPAD_DEV void extend_all_group(const DevIndex& ix, const BiIv& in, BiIv out[4], int gl) {
+  if (G < 8) { extend_all<WIDE>(ix, in, out); return; }
+  const int role = gl & 7, blk = role >> 2, q = role & 3;  // q: which quarter of the block's code words
+  const bool have_lo = in.lower != 0;
+  const uint64_t r_lo = have_lo ? in.lower - 1 : 0, r_hi = in.lower + in.size - 1;
+  const uint64_t r = blk ? r_hi : r_lo;
+  // this lane's code words
+  uint32_t nC = 0, nG = 0, nT = 0;
+  if (!WIDE) {
+    const uint8_t* p = ix.occ() + (r >> 6) * 32;
+    const int npos = (int)(r & 63) + 1;
+#if defined(__CUDA_ARCH__)
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + 16) + q);
+#else
+    const uint32_t w = (reinterpret_cast<const uint32_t*>(p + 16))[q];
+#endif
+    count_word(w, npos - 16 * q, nC, nG, nT);
+  } else {
+    const uint8_t* p = ix.occ() + (r >> 7) * 64;
+    const int npos = (int)(r & 127) + 1;
+#if defined(__CUDA_ARCH__)
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(p + 32) + q);
+    const uint32_t w0 = w.x, w1 = w.y;
+#else
+    const uint32_t w0 = (reinterpret_cast<const uint32_t*>(p + 32))[2 * q], w1 = (reinterpret_cast<const uint32_t*>(p + 32))[2 * q + 1];
+#endif
+    count_word(w0, npos - 32 * q, nC, nG, nT);
+    count_word(w1, npos - 32 * q - 16, nC, nG, nT);
+  }
+  uint32_t packed = nC | (nG << 10) | (nT << 20);  // each count <= 128
+#if defined(__CUDA_ARCH__)
+  packed += Grp<G>::shfl_xor(packed, 1);
+  packed += Grp<G>::shfl_xor(packed, 2);
+  const uint32_t other = Grp<G>::shfl_xor(packed, 4);
+#else
+  packed += Grp<G>::shfl_xor_self(packed, 1, gl);
+  packed += Grp<G>::shfl_xor_self(packed, 2, gl);
+  const uint32_t other = Grp<G>::shfl_xor_self(packed, 4, gl);
+#endif
+  const uint32_t p_lo = blk ? other : packed, p_hi = blk ? packed : other;
+  // per block: base counts + partial counts + the '$' / 'X' corrections of occ_finish
+  uint64_t lo[4] = {0, 0, 0, 0}, hi[4];
+  uint64_t s_lo = 0;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    if (b == 0 && !have_lo) continue;
+    const uint64_t rr = b ? r_hi : r_lo;
+    const uint32_t pk = b ? p_hi : p_lo;
+    uint64_t* c = b ? hi : lo;
+    const uint32_t cC = pk & 1023u, cG = (pk >> 10) & 1023u, cT = pk >> 20;
+    uint64_t bstart;
+    int npos;
+    bool flagged;
+    if (!WIDE) {
+      const U4 cn = load16(ix.occ() + (rr >> 6) * 32);
+      bstart = (rr >> 6) << 6; npos = (int)(rr & 63) + 1;
+      flagged = (cn.x >> 31) != 0;
+      c[0] = cn.x & 0x7fffffffu; c[1] = cn.y; c[2] = cn.z; c[3] = cn.w;
+    } else {
+      const uint8_t* p = ix.occ() + (rr >> 7) * 64;
+      const U4 c0 = load16(p), c1 = load16(p + 16);
+      bstart = (rr >> 7) << 7; npos = (int)(rr & 127) + 1;
+      const uint64_t a0 = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
+      flagged = (a0 >> 63) != 0;
+      c[0] = a0 & 0x7fffffffffffffffull;
+      c[1] = (uint64_t)c0.z | ((uint64_t)c0.w << 32);
+      c[2] = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
+      c[3] = (uint64_t)c1.z | ((uint64_t)c1.w << 32);
+    }
+    uint32_t nA = (uint32_t)npos - cC - cG - cT;
+    const uint64_t s0 = ix.m.sentinel_rows[0], s1 = ix.m.sentinel_rows[1];
+    nA -= (uint32_t)(s0 >= bstart && s0 <= rr);
+    nA -= (uint32_t)(s1 >= bstart && s1 <= rr);
+    if (flagged) {
+      const uint64_t upto = x_rows_upto(ix, rr);
+      const uint64_t before = bstart == 0 ? 0 : x_rows_upto(ix, bstart - 1);
+      nA -= (uint32_t)(upto - before);
+    }
+    c[0] += nA; c[1] += cC; c[2] += cG; c[3] += cT;
+  }
+  if (have_lo) s_lo = sentinels_upto(ix, r_lo);
+  uint64_t l = in.lower_rev + (sentinels_upto(ix, r_hi) - s_lo);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = 3 - k;
+    const uint64_t sz = hi[c] - lo[c];
+    out[k].lower = ix.m.less[c + 1] + lo[c];
+    out[k].lower_rev = l;
+    out[k].size = sz;
+    l += sz;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // One read's search, executed by the G lanes of a group.  Memory discipline: the sequential state that lives in
 // registers (heap length, slab cursors, best hit) is computed identically by every lane; heap entries, tree nodes and
@@ -369,26 +466,33 @@ struct GroupSearch {
   // min level looks at its two children and four grandchildren, which the family layout spreads over three lines (the
   // children sit in the line the node itself lives in); all six are fetched in one round trip by every lane.
   MAPAD_DEV void trickle_min(HeapEnt e, uint32_t n) {
+    // h: 1-based position on a min level with `e` in the hole.  Its children 2h, 2h+1 are the entries c0, c1 stored at
+    // cp[0], cp[1]; its grandchildren 4h .. 4h+3 are slots 0, 1 of the family lines of 2h and 2h+1 (two consecutive lines),
+    // whose slots 2 .. 5 hold the children of those grandchildren, i.e. the c0, c1 of the next step: two line loads per step.
     uint32_t h = 1u;
+    HeapEnt* hpos = ws.top;
+    HeapEnt* cp = ws.top + 1;
+    HeapEnt c0 = ws.top[1], c1 = ws.top[2];
+    uint32_t c_lo = 1u;  // C(level of the children of h)
     bool synced = false;
     while (2u * h <= n) {
-      HeapEnt x[6];
+      const uint32_t la = 2u * h - c_lo;
+      HeapEnt* pa = ws.line_ptr(la);
+      HeapEnt* pb = ws.line_ptr(la + 1u);
+      HeapLine6 fa, fb;
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
-        x[c] = e;
-        if (idx <= n) x[c] = rd(idx);
-      }
+      for (int c = 0; c < 6; ++c) { fa.x[c] = e; fb.x[c] = e; }
+      if (4u * h <= n) fa = load_line6(pa);
+      if (4u * h + 2u <= n) fb = load_line6(pb);
       if (MAPAD_TRICKLE_PREFETCH && G >= 8 && ws.gl < 8) {
-        // the next step (at one of the four grandchildren g) reads the two family lines of g's children: eight candidates
-        const uint32_t child = 2u * (4u * h + ((uint32_t)ws.gl >> 1)) + ((uint32_t)ws.gl & 1u);
-        if (2u * child <= n) {
-          const uint32_t cline = heap_loc(2u * child).line;
-          if (cline >= (uint32_t)TOPL) prefetch_line(ws.line_ptr(cline));
-        }
+        // the next step (at grandchild g) reads the family lines of 2g and 2g+1: eight candidates, one per lane
+        const uint32_t g = 4u * h + ((uint32_t)ws.gl >> 1);
+        const uint32_t gline = 2u * g - ((c_lo << 2) | 1u) + ((uint32_t)ws.gl & 1u);
+        if (4u * g + 2u * ((uint32_t)ws.gl & 1u) <= n && gline >= (uint32_t)TOPL) prefetch_line(ws.line_ptr(gline));
       }
       Grp<G>::sync();
       synced = true;
+      const HeapEnt x[6] = {c0, c1, fa.x[0], fa.x[1], fb.x[0], fb.x[1]};
       int best = -1;
       float bk = e.score;
 #pragma unroll
@@ -400,15 +504,24 @@ struct GroupSearch {
       HeapEnt be = x[0];
 #pragma unroll
       for (int c = 1; c < 6; ++c) if (best == c) be = x[c];
-      wr(ptr(h), be);
-      if (best < 2) { h = 2u * h + (uint32_t)best; break; }
-      const int pc = (best - 2) >> 1;
-      const HeapEnt pe = pc == 0 ? x[0] : x[1];
-      h = 4u * h + (uint32_t)(best - 2);
-      if (pe.score < e.score) { wr(ptr(h >> 1), e); e = pe; }
+      wr(hpos, be);
+      if (best < 2) { hpos = cp + best; break; }
+      const int gb = best - 2;                     // which grandchild
+      const HeapEnt pe = gb < 2 ? c0 : c1;          // its parent is one of the two children
+      HeapEnt* ppos = cp + (gb >> 1);
+      HeapEnt* gp = gb < 2 ? pa : pb;               // line of the chosen grandchild: slot gb & 1
+      hpos = gp + (gb & 1);
+      if (pe.score < e.score) { wr(ppos, e); e = pe; }
+      // the children of the chosen grandchild: slots 2 + 2 (gb & 1), 3 + 2 (gb & 1) of the same line
+      const HeapLine6& f = gb < 2 ? fa : fb;
+      c0 = (gb & 1) ? f.x[4] : f.x[2];
+      c1 = (gb & 1) ? f.x[5] : f.x[3];
+      cp = gp + 2 + 2 * (gb & 1);
+      h = 4u * h + (uint32_t)gb;
+      c_lo = (c_lo << 2) | 1u;
     }
     if (!synced) Grp<G>::sync();
-    wr(ptr(h), e);
+    wr(hpos, e);
   }
 
   // MinMaxHeap::push of `e` + Tree::add_node of `nd` (the two writes of an accepted child).
@@ -579,7 +692,7 @@ struct GroupSearch {
     BiIv ext[4];
     {
       const BiIv in = forward ? BiIv{sf.iv.lower_rev, sf.iv.lower, sf.iv.size} : sf.iv;
-      extend_all<WIDE>(ix, in, ext);
+      extend_all_group<WIDE, G>(ix, in, ext, ws.gl);
     }
     const bool del_ok = !bound_reject(bc, fadd(deletion_score, lower_bound));
     const int dist5 = forward ? j : j + 1;

@@ -55,6 +55,7 @@ struct Sched {
   void* main_sp = nullptr;
   int current = -1;
   int group_size = 1;
+  unsigned long long yields = 0;  // explicit back-off yields (a lane polling for a resource is not a divergence stall)
 };
 
 thread_local Sched* g_sched = nullptr;
@@ -120,6 +121,7 @@ void run(int n_groups, int group_size, const std::function<void(int, int)>& fn) 
     uint32_t gens = 0;
     for (auto& g : s.groups) gens += g.gen;
     const size_t before = remaining;
+    const unsigned long long yields_before = s.yields;
     for (size_t k = 0; k < s.lanes.size(); ++k) {
       const size_t i = reverse ? s.lanes.size() - 1 - k : k;
       LaneCtx& c = s.lanes[i];
@@ -130,7 +132,7 @@ void run(int n_groups, int group_size, const std::function<void(int, int)>& fn) 
     }
     uint32_t gens2 = 0;
     for (auto& g : s.groups) gens2 += g.gen;
-    idle_rounds = (gens2 == gens && remaining == before) ? idle_rounds + 1 : 0;
+    idle_rounds = (gens2 == gens && remaining == before && s.yields == yields_before) ? idle_rounds + 1 : 0;
     if (idle_rounds > 1000) {  // no barrier completed and no lane finished: the lanes of a group have diverged
       fprintf(stderr, "simt_emu: stall (divergent collectives)\n");
       for (auto& c : s.lanes) {
@@ -175,7 +177,7 @@ uint32_t mapad_simt_emu_ballot(int pred, int group_size) {
 }
 
 void mapad_simt_emu_yield(void) {
-  if (g_sched) yield_to_main();
+  if (g_sched) { g_sched->yields += 1; yield_to_main(); }
 }
 
 void mapad_simt_emu_sync(int group_size) {

@@ -22,7 +22,10 @@ from ref_cases import cli_params  # noqa: E402
 cfg = workloads.CONFIGS["cfg3"]
 genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
 index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234, device=0)
-mapper = api.Mapper(index, product_params(cli_params(cfg["library"])), device=0)
+spec = dict(cli_params(cfg["library"]))
+if os.environ.get("MAPAD_PROFILE_LIMITS"):  # e.g. "20000,100000": small STACK_LIMIT / EDIT_TREE_LIMIT -> many reads in limit recovery
+    spec["limits"] = tuple(int(x) for x in os.environ["MAPAD_PROFILE_LIMITS"].split(","))
+mapper = api.Mapper(index, product_params(spec), device=0)
 len_range = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else cfg["len_range"]
 seq, qual, off = workloads.simulate_batch(genome, 250_000, len_range, seed=79, library=cfg["library"])
 R, keep = api.make_reads(seq, qual, off, np.arange(250_000, dtype=np.uint32))
