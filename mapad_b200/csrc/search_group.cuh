@@ -887,11 +887,17 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
 }
 
 #if defined(__CUDACC__)
+// One warp per block: a block's registers and shared memory stay allocated until its LAST group has finished, and the
+// heaviest reads run for seconds after the queue is empty — with 128-thread blocks every such read would pin a quarter of
+// an SM's resident capacity while the launches of the next chunks wait for block slots.
 #ifndef MAPAD_GROUP_BLOCK
-#define MAPAD_GROUP_BLOCK 128
+#define MAPAD_GROUP_BLOCK 32
+#endif
+#ifndef MAPAD_GROUP_MIN_BLOCKS
+#define MAPAD_GROUP_MIN_BLOCKS 16
 #endif
 template <bool WIDE, int G, int TOPL>
-__global__ void __launch_bounds__(MAPAD_GROUP_BLOCK) k_search_group(const __grid_constant__ GroupLaunch<WIDE> a) {
+__global__ void __launch_bounds__(MAPAD_GROUP_BLOCK, MAPAD_GROUP_MIN_BLOCKS) k_search_group(const __grid_constant__ GroupLaunch<WIDE> a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t group_in_block = threadIdx.x / G;
   const uint32_t slot = blockIdx.x * (MAPAD_GROUP_BLOCK / G) + group_in_block;
