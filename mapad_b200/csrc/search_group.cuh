@@ -36,9 +36,26 @@ namespace mapad {
 struct GChunkPool {
   uint8_t* base;
   uint32_t n_chunks;
-  unsigned long long* heads;  // MAPAD_GPOOL_SHARDS x MAPAD_GPOOL_HEAD_STRIDE words
+  unsigned long long* heads;  // MAPAD_GPOOL_SHARDS x MAPAD_GPOOL_HEAD_STRIDE words; word 8 of shard 0: the pressure deadline
   uint32_t* next;
 };
+// Admission control.  A group that finds the whole pool empty while its read needs a chunk publishes "pressure until
+// now + 2 ms" (and keeps renewing it while it waits); groups about to START a read hold back while pressure is on.
+// Reads in flight then finish and free memory instead of competing with newcomers that would only be handed back later
+// (measured on hg19-scale chunks without it: 5 % of the reads were deferred and re-run, profiles/r2_summary.md).
+#define MAPAD_PRESSURE_HOLD_NS 2000000ull
+MAPAD_DEV unsigned long long dev_now_ns() {
+#if defined(__CUDA_ARCH__)
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#else
+  static unsigned long long fake = 0;
+  fake += 1000;
+  return fake;
+#endif
+}
+MAPAD_DEV volatile unsigned long long* gpool_pressure(const GChunkPool& p) { return reinterpret_cast<volatile unsigned long long*>(p.heads + 8); }
 
 MAPAD_DEV uint32_t gpool_pop(const GChunkPool& p, uint32_t shard) {
   unsigned long long* head = p.heads + (size_t)shard * MAPAD_GPOOL_HEAD_STRIDE;
@@ -87,6 +104,7 @@ MAPAD_DEV void gpool_release(const GChunkPool& p, uint32_t idx, uint32_t hint) {
 // host-side helper shared with the emulation harness: chunk i starts in shard i % SHARDS
 inline void gpool_init_host(uint32_t n_chunks, unsigned long long* heads, uint32_t* next) {
   for (uint32_t s = 0; s < MAPAD_GPOOL_SHARDS; ++s) heads[(size_t)s * MAPAD_GPOOL_HEAD_STRIDE] = s < n_chunks ? s : MAPAD_GPOOL_EMPTY;
+  heads[8] = 0ull;  // pressure deadline
   for (uint32_t i = 0; i < n_chunks; ++i) next[i] = i + MAPAD_GPOOL_SHARDS < n_chunks ? i + MAPAD_GPOOL_SHARDS : MAPAD_GPOOL_EMPTY;
 }
 
@@ -197,6 +215,7 @@ struct GroupWorkspace {
     if (gl == 0) {
       got = gpool_acquire(pool, shard);
       for (uint32_t w = 0; got == MAPAD_GPOOL_EMPTY && w < patience; ++w) {
+        *gpool_pressure(pool) = dev_now_ns() + MAPAD_PRESSURE_HOLD_NS;  // newcomers hold back while this group waits
         dev_backoff<G>();
         got = gpool_acquire(pool, shard);
       }
@@ -384,9 +403,9 @@ MAPAD_DEV void extend_all_group(const DevIndex& ix, const BiIv& in, BiIv out[4],
 // Speculative prefetch of the heap lines the NEXT trickle-down step may need (it depends on which grandchild wins): with
 // at least four lanes per read, lane b asks for the family line of grandchild b while the current step is being decided,
 // so a descent through the pooled (HBM / L2) levels costs one memory latency per TWO steps.  Costs up to 4x the line
-// traffic of those levels; build with -DMAPAD_TRICKLE_PREFETCH=0 to compare.
+// traffic of those levels and ~25 instructions per step; off by default, build with -DMAPAD_TRICKLE_PREFETCH=1 to compare.
 #ifndef MAPAD_TRICKLE_PREFETCH
-#define MAPAD_TRICKLE_PREFETCH 1
+#define MAPAD_TRICKLE_PREFETCH 0  // measured (profiles/r2_summary.md): the kernel is issue-bound, the extra address arithmetic costs more than it hides
 #endif
 MAPAD_DEV void prefetch_line(const void* p) {
 #if defined(__CUDA_ARCH__)
@@ -442,10 +461,16 @@ struct GroupSearch {
       synced = true;
       int best = -1;
       float bk = e.score;
+      if (4u * h + 3u <= n) {  // all six candidates exist (every step but the last one or two of a descent)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
-        if (idx <= n && f.x[c].score > bk) { best = c; bk = f.x[c].score; }
+        for (int c = 0; c < 6; ++c)
+          if (f.x[c].score > bk) { best = c; bk = f.x[c].score; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
+          if (idx <= n && f.x[c].score > bk) { best = c; bk = f.x[c].score; }
+        }
       }
       if (best < 0) break;
       const HeapEnt be = f.x[best];
@@ -478,7 +503,8 @@ struct GroupSearch {
     while (2u * h <= n) {
       const uint32_t la = 2u * h - c_lo;
       HeapEnt* pa = ws.line_ptr(la);
-      HeapEnt* pb = ws.line_ptr(la + 1u);
+      // la is odd and TOPL is odd: the next line is adjacent in memory unless it starts a new chunk
+      HeapEnt* pb = (la + 1u == (uint32_t)TOPL || ((la + 1u) & ((1u << WS::LPC_SHIFT) - 1u)) == 0u) ? ws.line_ptr(la + 1u) : pa + 8;
       HeapLine6 fa, fb;
 #pragma unroll
       for (int c = 0; c < 6; ++c) { fa.x[c] = e; fb.x[c] = e; }
@@ -495,10 +521,16 @@ struct GroupSearch {
       const HeapEnt x[6] = {c0, c1, fa.x[0], fa.x[1], fb.x[0], fb.x[1]};
       int best = -1;
       float bk = e.score;
+      if (4u * h + 3u <= n) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
-        if (idx <= n && x[c].score < bk) { best = c; bk = x[c].score; }
+        for (int c = 0; c < 6; ++c)
+          if (x[c].score < bk) { best = c; bk = x[c].score; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const uint32_t idx = c < 2 ? 2u * h + (uint32_t)c : 4u * h + (uint32_t)(c - 2);
+          if (idx <= n && x[c].score < bk) { best = c; bk = x[c].score; }
+        }
       }
       if (best < 0) break;
       HeapEnt be = x[0];
@@ -811,7 +843,11 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
   while (true) {
     if (!have) {
       uint32_t w = 0;
-      if (gl == 0) w = dev_atomic_add(&a.cur->queue_head, 1u);
+      if (gl == 0) {
+        // admission control: do not start a read while groups in flight are waiting for memory (bounded: 30 s)
+        for (uint32_t k = 0; k < 15000000u && *gpool_pressure(a.pool) > dev_now_ns(); ++k) dev_backoff<G>();
+        w = dev_atomic_add(&a.cur->queue_head, 1u);
+      }
       w = Grp<G>::shfl(w, 0);
       if (w >= a.n_work) break;
       r = a.work_list ? a.work_list[w] : w;
@@ -830,11 +866,14 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
       gs.begin(a.ix, split);
       have = true;
     }
-    {  // patience grows with the work already invested in this read (2 us per popped frame, at least 0.4 ms)
-      const uint32_t p = gs.frames < 200u ? 200u : gs.frames;
-      ws.patience = a.patient ? MAPAD_PATIENCE_MAX : (p < MAPAD_PATIENCE_MAX ? p : MAPAD_PATIENCE_MAX);
+    {  // patience grows with the work already invested in this read: 10 back-off rounds (20 us, about what a frame costs on a
+       // saturated GPU) per popped frame, at least 4 ms — young reads step aside first, old ones wait for their memory
+      const uint32_t f = gs.frames < 200u ? 200u : gs.frames;
+      const uint32_t p = f < MAPAD_PATIENCE_MAX / 10u ? f * 10u : MAPAD_PATIENCE_MAX;
+      ws.patience = a.patient ? MAPAD_PATIENCE_MAX : p;
 #if !defined(__CUDA_ARCH__)
       if (G == 1) ws.patience = 0;  // the emulation runs per-thread groups one after the other: nobody to wait for
+      else if (!a.patient && ws.patience > 2000u) ws.patience = 2000u;  // keep the emulated waits short
 #endif
     }
     const int rc = gs.step(a.ix, a.P, job);
@@ -909,6 +948,7 @@ __global__ void k_gpool_init(GChunkPool p) {  // chunk i starts in shard i % SHA
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.n_chunks) p.next[i] = i + MAPAD_GPOOL_SHARDS < p.n_chunks ? i + MAPAD_GPOOL_SHARDS : MAPAD_GPOOL_EMPTY;
   if (i < MAPAD_GPOOL_SHARDS) p.heads[(size_t)i * MAPAD_GPOOL_HEAD_STRIDE] = i < p.n_chunks ? (unsigned long long)i : (unsigned long long)MAPAD_GPOOL_EMPTY;
+  if (i == 0) p.heads[8] = 0ull;  // pressure deadline
 }
 #endif
 
