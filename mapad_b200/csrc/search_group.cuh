@@ -171,101 +171,8 @@ MAPAD_DEV float u32_as_f32(uint32_t u) {
 template <bool WIDE> struct GNodeOf { using type = NodeT<false>; };
 template <> struct GNodeOf<true> { using type = NodeW32; };
 
-// Workspace of one group (search_core.cuh's workspace concept).  Every lane of the group holds the same copy and makes
-// the same calls; pool operations are done once, by lane 0, and broadcast.
-template <bool WIDE, int G, int TOPL>
-struct GroupWorkspace {
-  using Node = typename GNodeOf<WIDE>::type;
-  static constexpr uint32_t NPC_SHIFT = MAPAD_GCHUNK_SHIFT - 5u;  // nodes per chunk (32 B each)
-  static constexpr uint32_t LPC_SHIFT = MAPAD_GCHUNK_SHIFT - 6u;  // heap lines per chunk (64 B each)
-  GChunkPool pool;
-  uint32_t* table;       // this group's chunk table: [0, nt) node chunks, [nt, nt + ht) heap chunks
-  uint32_t nt, ht;
-  uint32_t n_node_chunks, n_heap_chunks;
-  Node* node0;           // chunk 0 of each kind is owned for good: no table lookup for small searches
-  HeapEnt* heap0;
-  HeapEnt* top;          // shared memory: TOPL lines of 8 entries
-  HitTmp* hits;
-  uint32_t max_nodes, max_heap;
-  uint32_t patience;     // how long (in 2 us back-off rounds) this group waits for a chunk when the pool is dry
-  uint32_t shard;        // this group's home shard of the pool
-  int gl;                // lane in group
-
-  MAPAD_DEV Node& node(uint32_t id) const {
-    if (id < (1u << NPC_SHIFT)) return node0[id];
-    const uint32_t c = table[id >> NPC_SHIFT];
-    return reinterpret_cast<Node*>(pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT))[id & ((1u << NPC_SHIFT) - 1u)];
-  }
-  MAPAD_DEV HeapEnt* line_ptr(uint32_t line) const {
-    if (line < (uint32_t)TOPL) return top + (line << 3);
-    const uint32_t g = line;  // the pooled storage is addressed by the plain line number (lines < TOPL unused there)
-    if (g < (1u << LPC_SHIFT)) return heap0 + ((size_t)g << 3);
-    const uint32_t c = table[nt + (g >> LPC_SHIFT)];
-    return reinterpret_cast<HeapEnt*>(pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT)) + ((size_t)(g & ((1u << LPC_SHIFT) - 1u)) << 3);
-  }
-  MAPAD_DEV HeapEnt* slot_ptr(uint32_t i0) const {  // 0-based logical index
-    const HLoc l = heap_loc(i0 + 1u);
-    return line_ptr(l.line) + l.slot;
-  }
-  // The pool is shared by every group of every launch on the device.  When it is dry the group waits for chunks that
-  // finishing reads give back — the longer, the more work its own read has already absorbed (patience is set by the caller
-  // in proportion to the frames popped so far), so that young reads step aside first (they are handed back and re-run).
-  MAPAD_DEV uint32_t acquire_chunk() const {
-    uint32_t got = MAPAD_GPOOL_EMPTY;
-    if (gl == 0) {
-      got = gpool_acquire(pool, shard);
-      for (uint32_t w = 0; got == MAPAD_GPOOL_EMPTY && w < patience; ++w) {
-        *gpool_pressure(pool) = dev_now_ns() + MAPAD_PRESSURE_HOLD_NS;  // newcomers hold back while this group waits
-        dev_backoff<G>();
-        got = gpool_acquire(pool, shard);
-      }
-    }
-    return Grp<G>::shfl(got, 0);
-  }
-  MAPAD_DEV bool ensure_node(uint32_t id) {
-    if (id >= max_nodes) return false;
-    const uint32_t c = id >> NPC_SHIFT;
-    if (c < n_node_chunks) return true;
-    if (c >= nt) return false;
-    const uint32_t got = acquire_chunk();
-    if (got == MAPAD_GPOOL_EMPTY) return false;
-    table[c] = got;
-    n_node_chunks = c + 1;
-    return true;
-  }
-  MAPAD_DEV bool ensure_heap(uint32_t n0) {  // room for logical index n0
-    if (n0 >= max_heap) return false;
-    const HLoc l = heap_loc(n0 + 1u);
-    if (l.line < (uint32_t)TOPL) return true;
-    const uint32_t c = l.line >> LPC_SHIFT;
-    if (c < n_heap_chunks) return true;
-    if (c >= ht) return false;
-    const uint32_t got = acquire_chunk();
-    if (got == MAPAD_GPOOL_EMPTY) return false;
-    table[nt + c] = got;
-    n_heap_chunks = c + 1;
-    return true;
-  }
-  MAPAD_DEV uint32_t min_cap() const { return max_nodes; }
-  MAPAD_DEV void release_base() const {  // group exit: the two base chunks go back to the pool
-    if (gl == 0) { gpool_release(pool, table[0], shard); gpool_release(pool, table[nt], shard); }
-  }
-  MAPAD_DEV void release_extra() {  // keep chunk 0 of each kind
-    if (gl == 0) {
-      for (uint32_t c = n_node_chunks; c > 1; --c) gpool_release(pool, table[c - 1], shard);
-      for (uint32_t c = n_heap_chunks; c > 1; --c) gpool_release(pool, table[nt + c - 1], shard);
-    }
-    n_node_chunks = 1;
-    n_heap_chunks = 1;
-  }
-  struct Store {
-    const GroupWorkspace* w;
-    MAPAD_DEV HeapEnt get(uint32_t i) const { return *w->slot_ptr(i); }
-    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { *w->slot_ptr(i) = e; }
-  };
-  MAPAD_DEV Store heap() const { return Store{this}; }
-};
-
+#define MAPAD_POOL_TIMEOUT_FLAG 4u   // Cursors::overflow bit: a group found no base chunks within the start-up patience
+#define MAPAD_PATIENCE_MAX 10000000u // back-off rounds of 2 us: 20 s
 // Everything one launch needs (passed by value as the kernel parameter).
 template <bool WIDE>
 struct GroupLaunch {
@@ -293,51 +200,159 @@ struct GroupLaunch {
   uint32_t flags_or;       // ORed into ReadMid::flags (bit 1: the read went through a retry launch)
   uint32_t patient;        // 1: never hand a read back, wait for the pool (last-resort launches)
 };
-#define MAPAD_POOL_TIMEOUT_FLAG 4u   // Cursors::overflow bit: a group found no base chunks within the start-up patience
-#define MAPAD_PATIENCE_MAX 10000000u // back-off rounds of 2 us: 20 s
+
+
+// Workspace of one group (search_core.cuh's workspace concept).  Every lane of the group holds the same copy and makes
+// the same calls; pool operations are done once, by lane 0, and broadcast.
+template <bool WIDE, int G, int TOPL>
+struct GroupWorkspace {
+  using Node = typename GNodeOf<WIDE>::type;
+  static constexpr uint32_t NPC_SHIFT = MAPAD_GCHUNK_SHIFT - 5u;  // nodes per chunk (32 B each)
+  static constexpr uint32_t LPC_SHIFT = MAPAD_GCHUNK_SHIFT - 6u;  // heap lines per chunk (64 B each)
+  // launch-wide constants are read through `a` (kernel parameter space) instead of being copied into registers
+  const GroupLaunch<WIDE>* a;
+  uint32_t slot;         // this group's number: selects its chunk table, hit array and home shard of the pool
+  uint32_t frames;       // frames popped so far by the current read (also sets the patience when the pool is dry)
+  uint32_t n_node_chunks, n_heap_chunks;
+  Node* node0;           // chunk 0 of each kind is owned for good: no table lookup for small searches
+  HeapEnt* heap0;
+  HeapEnt* top;          // shared memory: TOPL lines of 8 entries
+  int gl;                // lane in group
+
+  // chunk table of this group: [0, nt) node chunks, [nt, nt + ht) heap chunks
+  MAPAD_DEV uint32_t* table() const { return a->tables + (size_t)slot * (a->nt + a->ht); }
+  MAPAD_DEV HitTmp* hits() const { return a->hit_base + (size_t)slot * MAPAD_MAX_HITS; }
+  MAPAD_DEV uint32_t shard() const { return (slot * 2654435761u) >> 24; }  // spreads neighbouring groups over the 256 shards
+  // How long (in 2 us back-off rounds) the group waits for a chunk when the pool is dry: 10 rounds (20 us, about what a
+  // frame costs on a saturated GPU) per frame already popped, at least 4 ms — young reads step aside first.
+  MAPAD_DEV uint32_t patience() const {
+    if (a->patient || frames >= MAPAD_PATIENCE_MAX / 10u) return MAPAD_PATIENCE_MAX;
+    uint32_t p = (frames < 200u ? 200u : frames) * 10u;
+#if !defined(__CUDA_ARCH__)
+    if (G == 1) p = 0;               // the emulation runs per-thread groups one after the other: nobody to wait for
+    else if (p > 2000u) p = 2000u;   // keep the emulated waits short
+#endif
+    return p;
+  }
+
+  MAPAD_DEV Node& node(uint32_t id) const {
+    if (id < (1u << NPC_SHIFT)) return node0[id];
+    const uint32_t c = table()[id >> NPC_SHIFT];
+    return reinterpret_cast<Node*>(a->pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT))[id & ((1u << NPC_SHIFT) - 1u)];
+  }
+  MAPAD_DEV HeapEnt* line_ptr(uint32_t line) const {
+    if (line < (uint32_t)TOPL) return top + (line << 3);
+    const uint32_t g = line;  // the pooled storage is addressed by the plain line number (lines < TOPL unused there)
+    if (g < (1u << LPC_SHIFT)) return heap0 + ((size_t)g << 3);
+    const uint32_t c = table()[a->nt + (g >> LPC_SHIFT)];
+    return reinterpret_cast<HeapEnt*>(a->pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT)) + ((size_t)(g & ((1u << LPC_SHIFT) - 1u)) << 3);
+  }
+  MAPAD_DEV HeapEnt* slot_ptr(uint32_t i0) const {  // 0-based logical index
+    const HLoc l = heap_loc(i0 + 1u);
+    return line_ptr(l.line) + l.slot;
+  }
+  // The pool is shared by every group of every launch on the device.  When it is dry the group waits for chunks that
+  // finishing reads give back — the longer, the more work its own read has already absorbed (patience is set by the caller
+  // in proportion to the frames popped so far), so that young reads step aside first (they are handed back and re-run).
+  MAPAD_DEV uint32_t acquire_chunk() const {
+    uint32_t got = MAPAD_GPOOL_EMPTY;
+    if (gl == 0) {
+      got = gpool_acquire(a->pool, shard());
+      if (got == MAPAD_GPOOL_EMPTY) {
+        const uint32_t rounds = patience();
+        for (uint32_t w = 0; got == MAPAD_GPOOL_EMPTY && w < rounds; ++w) {
+          *gpool_pressure(a->pool) = dev_now_ns() + MAPAD_PRESSURE_HOLD_NS;  // newcomers hold back while this group waits
+          dev_backoff<G>();
+          got = gpool_acquire(a->pool, shard());
+        }
+      }
+    }
+    return Grp<G>::shfl(got, 0);
+  }
+  MAPAD_DEV bool ensure_node(uint32_t id) {
+    if (id >= a->max_nodes) return false;
+    const uint32_t c = id >> NPC_SHIFT;
+    if (c < n_node_chunks) return true;
+    if (c >= a->nt) return false;
+    const uint32_t got = acquire_chunk();
+    if (got == MAPAD_GPOOL_EMPTY) return false;
+    table()[c] = got;
+    n_node_chunks = c + 1;
+    return true;
+  }
+  MAPAD_DEV bool ensure_heap(uint32_t n0) {  // room for logical index n0
+    if (n0 >= a->max_heap) return false;
+    const HLoc l = heap_loc(n0 + 1u);
+    if (l.line < (uint32_t)TOPL) return true;
+    const uint32_t c = l.line >> LPC_SHIFT;
+    if (c < n_heap_chunks) return true;
+    if (c >= a->ht) return false;
+    const uint32_t got = acquire_chunk();
+    if (got == MAPAD_GPOOL_EMPTY) return false;
+    table()[a->nt + c] = got;
+    n_heap_chunks = c + 1;
+    return true;
+  }
+  MAPAD_DEV uint32_t min_cap() const { return a->max_nodes; }
+  MAPAD_DEV void release_base() const {  // group exit: the two base chunks go back to the pool
+    if (gl == 0) { gpool_release(a->pool, table()[0], shard()); gpool_release(a->pool, table()[a->nt], shard()); }
+  }
+  MAPAD_DEV void release_extra() {  // keep chunk 0 of each kind
+    if (gl == 0) {
+      uint32_t* t = table();
+      for (uint32_t c = n_node_chunks; c > 1; --c) gpool_release(a->pool, t[c - 1], shard());
+      for (uint32_t c = n_heap_chunks; c > 1; --c) gpool_release(a->pool, t[a->nt + c - 1], shard());
+    }
+    n_node_chunks = 1;
+    n_heap_chunks = 1;
+  }
+  struct Store {
+    const GroupWorkspace* w;
+    MAPAD_DEV HeapEnt get(uint32_t i) const { return *w->slot_ptr(i); }
+    MAPAD_DEV void set(uint32_t i, HeapEnt e) const { *w->slot_ptr(i) = e; }
+  };
+  MAPAD_DEV Store heap() const { return Store{this}; }
+};
 
 // FmdExtIterator for a lane group (dev_index.cuh::extend_all, fmd_index.rs:117-182): the two occ blocks hold 8 (narrow) or
 // 16 (wide) words of 2-bit codes; with G >= 8 lanes 0..3 of every 8 count the words of the block of row lower - 1, lanes
-// 4..7 those of the block of row lower + size - 1, and three xor-shuffles give every lane both totals.
+// 4..7 those of the block of row lower + size - 1, and three xor-shuffles give every lane both totals (G = 4: two lanes
+// per block, two shuffles).
 template <bool WIDE, int G>
 MAPAD_DEV void extend_all_group(const DevIndex& ix, const BiIv& in, BiIv out[4], int gl) {
-  if (G < 8) { extend_all<WIDE>(ix, in, out); return; }
-  const int role = gl & 7, blk = role >> 2, q = role & 3;  // q: which quarter of the block's code words
+  if (G < 4) { extend_all<WIDE>(ix, in, out); return; }
+  constexpr int LPB = G >= 8 ? 4 : 2;          // lanes per block
+  constexpr int NW = WIDE ? 8 : 4;             // code words per block
+  constexpr int WPL = NW / LPB;                // words per lane
+  const int role = gl & (2 * LPB - 1), blk = role / LPB, q = role % LPB;
   const bool have_lo = in.lower != 0;
   const uint64_t r_lo = have_lo ? in.lower - 1 : 0, r_hi = in.lower + in.size - 1;
   const uint64_t r = blk ? r_hi : r_lo;
   // this lane's code words
   uint32_t nC = 0, nG = 0, nT = 0;
-  if (!WIDE) {
-    const uint8_t* p = ix.occ() + (r >> 6) * 32;
-    const int npos = (int)(r & 63) + 1;
+  {
+    const uint8_t* p = WIDE ? ix.occ() + (r >> 7) * 64 + 32 : ix.occ() + (r >> 6) * 32 + 16;
+    const int npos = WIDE ? (int)(r & 127) + 1 : (int)(r & 63) + 1;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(p) + q * WPL;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
 #if defined(__CUDA_ARCH__)
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p + 16) + q);
+      const uint32_t w = __ldg(wp + k);
 #else
-    const uint32_t w = (reinterpret_cast<const uint32_t*>(p + 16))[q];
+      const uint32_t w = wp[k];
 #endif
-    count_word(w, npos - 16 * q, nC, nG, nT);
-  } else {
-    const uint8_t* p = ix.occ() + (r >> 7) * 64;
-    const int npos = (int)(r & 127) + 1;
-#if defined(__CUDA_ARCH__)
-    const uint2 w = __ldg(reinterpret_cast<const uint2*>(p + 32) + q);
-    const uint32_t w0 = w.x, w1 = w.y;
-#else
-    const uint32_t w0 = (reinterpret_cast<const uint32_t*>(p + 32))[2 * q], w1 = (reinterpret_cast<const uint32_t*>(p + 32))[2 * q + 1];
-#endif
-    count_word(w0, npos - 32 * q, nC, nG, nT);
-    count_word(w1, npos - 32 * q - 16, nC, nG, nT);
+      count_word(w, npos - 16 * (q * WPL + k), nC, nG, nT);
+    }
   }
   uint32_t packed = nC | (nG << 10) | (nT << 20);  // each count <= 128
 #if defined(__CUDA_ARCH__)
   packed += Grp<G>::shfl_xor(packed, 1);
-  packed += Grp<G>::shfl_xor(packed, 2);
-  const uint32_t other = Grp<G>::shfl_xor(packed, 4);
+  if (LPB == 4) packed += Grp<G>::shfl_xor(packed, 2);
+  const uint32_t other = Grp<G>::shfl_xor(packed, LPB);
 #else
   packed += Grp<G>::shfl_xor_self(packed, 1, gl);
-  packed += Grp<G>::shfl_xor_self(packed, 2, gl);
-  const uint32_t other = Grp<G>::shfl_xor_self(packed, 4, gl);
+  if (LPB == 4) packed += Grp<G>::shfl_xor_self(packed, 2, gl);
+  const uint32_t other = Grp<G>::shfl_xor_self(packed, LPB, gl);
 #endif
   const uint32_t p_lo = blk ? other : packed, p_hi = blk ? packed : other;
   // per block: base counts + partial counts + the '$' / 'X' corrections of occ_finish
@@ -436,7 +451,7 @@ struct GroupSearch {
   uint32_t heap_n, node_hi, free_head, tree_len, n_hits;
   float best_score;    // hits[0] of the BinaryHeap (its maximum) while n_hits > 0
   uint64_t best_size;
-  uint32_t frames, limit_hit;
+  uint32_t limit_hit;
   bool overflow;
 
   MAPAD_DEV void wr(HeapEnt* p, HeapEnt e) const { if (ws.gl == 0) *p = e; }
@@ -626,7 +641,7 @@ struct GroupSearch {
 
   MAPAD_DEV void begin(const DevIndex& ix, int start_pos) {
     heap_n = 0; node_hi = 1; free_head = MAPAD_NO_NODE; tree_len = 1; n_hits = 0; best_score = 0.0f; best_size = 0;
-    frames = 0; limit_hit = 0; overflow = false;
+    ws.frames = 0; limit_hit = 0; overflow = false;
     Frame root;
     root.iv = BiIv{0, 0, ix.m.n};
     root.start = start_pos; root.len = 0; root.gap_f = GAP_CLOSED; root.gap_b = GAP_CLOSED; root.ngaps = 0;
@@ -661,13 +676,13 @@ struct GroupSearch {
           HitTmp h;
           h.score = f.score; h.node = id; h.lower = f.iv.lower; h.lower_rev = f.iv.lower_rev; h.size = f.iv.size;
           uint32_t nh = n_hits;
-          bh_push(ws.hits, nh, h);
+          bh_push(ws.hits(), nh, h);
         }
       }
       if (n_hits < MAPAD_MAX_HITS) n_hits += 1;
       Grp<G>::sync();
-      best_score = ws.hits[0].score;
-      best_size = ws.hits[0].size;
+      best_score = ws.hits()[0].score;
+      best_size = ws.hits()[0].size;
       return;
     }
     if (!ws.ensure_heap(heap_n)) { overflow = true; return; }
@@ -686,7 +701,7 @@ struct GroupSearch {
     if (n == 2) m = 2;
     else if (n >= 3) m = ws.top[1].score > ws.top[2].score ? 2u : 3u;
     const HeapEnt topent = ws.top[m - 1u];
-    frames += 1;
+    ws.frames += 1;
     const Node pn = ws.node(topent.node);  // issued before the heap is repaired: both latencies overlap
     const uint32_t n1 = n - 1u;
     if (m <= n1) {
@@ -809,32 +824,28 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
   using GS = GroupSearch<WIDE, G, TOPL>;
   GS gs;
   auto& ws = gs.ws;
-  ws.pool = a.pool;
-  ws.nt = a.nt; ws.ht = a.ht;
-  ws.table = a.tables + (size_t)slot * (a.nt + a.ht);
+  ws.a = &a;
+  ws.slot = slot;
   ws.gl = gl;
   // every group takes its two base chunks (nodes, heap) from the device-wide pool when it starts and returns them when it exits
-  ws.patience = MAPAD_PATIENCE_MAX;
-  ws.shard = (slot * 2654435761u) >> 24;  // spread neighbouring groups (and the launches in flight) over the 256 shards
+  ws.frames = MAPAD_PATIENCE_MAX;  // full patience while waiting for the base chunks
   const uint32_t c_nodes = ws.acquire_chunk();
   const uint32_t c_heap = c_nodes != MAPAD_GPOOL_EMPTY ? ws.acquire_chunk() : MAPAD_GPOOL_EMPTY;
   if (c_heap == MAPAD_GPOOL_EMPTY) {
     if (gl == 0) {
-      if (c_nodes != MAPAD_GPOOL_EMPTY) gpool_release(a.pool, c_nodes, ws.shard);
+      if (c_nodes != MAPAD_GPOOL_EMPTY) gpool_release(a.pool, c_nodes, ws.shard());
       dev_atomic_or(&a.cur->overflow, MAPAD_POOL_TIMEOUT_FLAG);
     }
     return;
   }
-  if (gl == 0) { ws.table[0] = c_nodes; ws.table[a.nt] = c_heap; }
+  if (gl == 0) { ws.table()[0] = c_nodes; ws.table()[a.nt] = c_heap; }
   Grp<G>::sync();
   ws.n_node_chunks = 1;
   ws.n_heap_chunks = 1;
   ws.node0 = reinterpret_cast<typename GS::Node*>(a.pool.base + ((size_t)c_nodes << MAPAD_GCHUNK_SHIFT));
   ws.heap0 = reinterpret_cast<HeapEnt*>(a.pool.base + ((size_t)c_heap << MAPAD_GCHUNK_SHIFT));
   ws.top = smem_top;
-  ws.hits = a.hit_base + (size_t)slot * MAPAD_MAX_HITS;
-  ws.max_nodes = a.max_nodes;
-  ws.max_heap = a.max_heap;
+  ws.frames = 0;
   uint32_t busy_iters = 0;
   bool have = false;
   uint32_t r = 0;
@@ -866,16 +877,6 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
       gs.begin(a.ix, split);
       have = true;
     }
-    {  // patience grows with the work already invested in this read: 10 back-off rounds (20 us, about what a frame costs on a
-       // saturated GPU) per popped frame, at least 4 ms — young reads step aside first, old ones wait for their memory
-      const uint32_t f = gs.frames < 200u ? 200u : gs.frames;
-      const uint32_t p = f < MAPAD_PATIENCE_MAX / 10u ? f * 10u : MAPAD_PATIENCE_MAX;
-      ws.patience = a.patient ? MAPAD_PATIENCE_MAX : p;
-#if !defined(__CUDA_ARCH__)
-      if (G == 1) ws.patience = 0;  // the emulation runs per-thread groups one after the other: nobody to wait for
-      else if (!a.patient && ws.patience > 2000u) ws.patience = 2000u;  // keep the emulated waits short
-#endif
-    }
     const int rc = gs.step(a.ix, a.P, job);
     busy_iters += 1;
     if (a.iter_budget && busy_iters >= a.iter_budget) { ws.release_extra(); break; }
@@ -894,7 +895,7 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
       if (gl == 0) hit_off = dev_atomic_add(&a.cur->hit_cursor, nh);
       hit_off = Grp<G>::shfl(hit_off, 0);
       for (uint32_t h = (uint32_t)gl; h < nh; h += (uint32_t)G) {
-        const HitTmp ht = ws.hits[h];
+        const HitTmp ht = ws.hits()[h];
         uint32_t n_left;
         const uint32_t total = path_length<WIDE>(ws, ht.node, split, n_left);
         const uint32_t op_off = dev_atomic_add(&a.cur->op_cursor, total);
@@ -913,7 +914,7 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
     if (gl == 0) {
       ReadMid m;
       m.hit_off = hit_off;
-      m.frames_popped = gs.frames;
+      m.frames_popped = ws.frames;
       m.flags = (gs.limit_hit ? 1u : 0u) | a.flags_or;
       m.n_hits = nh;
       a.mid[r] = m;
