@@ -269,8 +269,7 @@ int mapad_gpu_clone_to_device(mapad_gpu* src, int device, mapad_gpu** out);
 /* Announces how many handles the caller is about to create on `device`.  All handles of a device share ONE search
  * workspace (the chunk pool the per-read heaps / edit trees grow in — the thread-local scratch of mapping.rs:146-149),
  * allocated with the first handle: 75 % of the free device memory, but leaving 1 GiB per announced handle for their batch
- * buffers (MAPAD_WS_BYTES overrides the size).  The count is also taken as the number of batches in flight at once: each
- * launch then occupies its share of the GPU, so that all chunks advance together. */
+ * buffers.  MAPAD_WS_BYTES overrides the size. */
 int mapad_gpu_plan_handles(int device, int n_handles);
 int mapad_gpu_set_params(mapad_gpu* h, const mapad_params* params);
 int mapad_gpu_map_batch(mapad_gpu* h, const mapad_reads* in, uint32_t flags, mapad_results* out);

@@ -504,10 +504,13 @@ static int upload_batch(mapad_gpu* h, const mapad_reads* in) {
 // One launch maps every read of the batch; a read is only handed back (deferred) when the chunk pool runs dry, and
 // then re-run with fewer groups in flight, i.e. more pool per group.
 struct GroupShape { int g, topl; };
-static GroupShape group_shape() {  // tuning knobs, read per batch: MAPAD_GROUP = lanes per read, MAPAD_TOPL = heap lines in shared memory
-  GroupShape s{8, 11};
+static GroupShape group_shape(bool wide) {  // tuning knobs, read per batch: MAPAD_GROUP = lanes per read, MAPAD_TOPL = heap lines in shared memory
+  // defaults (profiles/r2_summary.md): small references (narrow layout, light reads) are issue-bound -> 4 lanes per read;
+  // hg19-scale references (wide layout, reads of 1e5 - 1e7 frames) are bound by pool capacity and by the latency of
+  // their heaviest reads -> one read per warp
+  GroupShape s{wide ? 32 : 4, 11};
   if (const char* e = getenv("MAPAD_GROUP")) s.g = atoi(e);
-  if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 32) s.g = 8;
+  if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 32) s.g = wide ? 32 : 4;
   s.topl = s.g == 1 ? 3 : (s.g == 32 ? 43 : 11);
   if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43) s.topl = t; }
   return s;
@@ -537,7 +540,7 @@ template <bool WIDE>
 static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams& P, const ReadBatch& rb, uint64_t& launches,
                               const std::function<void(const char*, uint64_t, uint64_t, uint64_t)>& trace) {
   const uint64_t n = h->n_reads;
-  GroupShape sh = group_shape();
+  GroupShape sh = group_shape(WIDE);
   if (sh.topl == 3 && sh.g != 1) sh.topl = 11;
   const uint32_t gpb = (uint32_t)(MAPAD_GROUP_BLOCK / sh.g);
   GroupLaunch<WIDE> a;
@@ -557,12 +560,19 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
   uint64_t per_sm = sh.g == 1 ? 512 : (sh.g == 32 ? 16 : (uint64_t)(512 / sh.g));
   if (const char* e = getenv("MAPAD_GROUPS_PER_SM")) per_sm = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
   uint64_t slots = per_sm * (uint64_t)h->n_sm;
-  // Fair share: with C launches announced to be in flight at once (mapad_gpu_plan_handles) every launch takes 1/C of the
-  // resident capacity (twice that, to fill the slots of launches that finish early).  All chunks then advance together and
-  // the heaviest reads of EVERY chunk start at once (longest-first order) instead of waiting for the block slots of the
-  // launches enqueued before them — measured on hg19-scale chunks: the last launch of 20 ended at 267 s instead of ~130 s.
-  const int conc = g_concurrency[h->device & 63];
-  if (conc > 1) slots = std::max<uint64_t>(4ull * gpb, 2ull * slots / (uint64_t)conc);
+  // Launch share.  With C launches announced to be in flight at once (mapad_gpu_plan_handles) a launch takes 2/C of the
+  // resident capacity, so that all chunks advance together and the heaviest reads of EVERY chunk start at once (longest-
+  // first order) instead of waiting for the block slots of the launches enqueued before them.  This only works while the
+  // reads in flight fit the pool: with G = 8 (9 472 reads in flight) on hg19-scale chunks it put the heavy reads of all
+  // chunks in flight at once, the pool ran dry and the run got 2-3x slower (profiles/r2_summary.md) — there one read per
+  // warp (G = 32, 2 368 reads in flight) is the setting that keeps the footprint inside the pool.
+  // MAPAD_LAUNCH_SHARE=<divisor> overrides (1 = every launch sized for the whole GPU).
+  {
+    const int conc = g_concurrency[h->device & 63];
+    uint64_t d = conc > 2 ? (uint64_t)conc / 2 : 1;
+    if (const char* e = getenv("MAPAD_LAUNCH_SHARE")) d = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    slots = std::max<uint64_t>(4ull * gpb, slots / d);
+  }
   if (const char* e = getenv("MAPAD_GROUPS")) slots = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
   slots = std::min<uint64_t>(slots, n_chunks / 4);  // two base chunks per group, at least half of the pool for growth
   const uint32_t profile_iters = getenv("MAPAD_PROFILE_ITERS") ? (uint32_t)strtoul(getenv("MAPAD_PROFILE_ITERS"), nullptr, 0) : 0u;

@@ -214,6 +214,7 @@ struct GroupWorkspace {
   uint32_t slot;         // this group's number: selects its chunk table, hit array and home shard of the pool
   uint32_t frames;       // frames popped so far by the current read (also sets the patience when the pool is dry)
   uint32_t n_node_chunks, n_heap_chunks;
+  uint32_t heap_hi;      // logical heap indices below this are known to be backed by memory
   Node* node0;           // chunk 0 of each kind is owned for good: no table lookup for small searches
   HeapEnt* heap0;
   HeapEnt* top;          // shared memory: TOPL lines of 8 entries
@@ -223,11 +224,12 @@ struct GroupWorkspace {
   MAPAD_DEV uint32_t* table() const { return a->tables + (size_t)slot * (a->nt + a->ht); }
   MAPAD_DEV HitTmp* hits() const { return a->hit_base + (size_t)slot * MAPAD_MAX_HITS; }
   MAPAD_DEV uint32_t shard() const { return (slot * 2654435761u) >> 24; }  // spreads neighbouring groups over the 256 shards
-  // How long (in 2 us back-off rounds) the group waits for a chunk when the pool is dry: 10 rounds (20 us, about what a
-  // frame costs on a saturated GPU) per frame already popped, at least 4 ms — young reads step aside first.
+  // How long (in 2 us back-off rounds) the group waits for a chunk when the pool is dry: one round per frame already
+  // popped, at least 0.4 ms — young reads step aside first.  (Ten rounds per frame were measured: reads then sleep on their
+  // memory for seconds and the GPU idles.)
   MAPAD_DEV uint32_t patience() const {
-    if (a->patient || frames >= MAPAD_PATIENCE_MAX / 10u) return MAPAD_PATIENCE_MAX;
-    uint32_t p = (frames < 200u ? 200u : frames) * 10u;
+    if (a->patient || frames >= MAPAD_PATIENCE_MAX) return MAPAD_PATIENCE_MAX;
+    uint32_t p = frames < 200u ? 200u : frames;
 #if !defined(__CUDA_ARCH__)
     if (G == 1) p = 0;               // the emulation runs per-thread groups one after the other: nobody to wait for
     else if (p > 2000u) p = 2000u;   // keep the emulated waits short
@@ -281,16 +283,18 @@ struct GroupWorkspace {
     return true;
   }
   MAPAD_DEV bool ensure_heap(uint32_t n0) {  // room for logical index n0
+    if (n0 < heap_hi) return true;           // backed before (the heap shrinks and regrows around its high-water mark)
     if (n0 >= a->max_heap) return false;
     const HLoc l = heap_loc(n0 + 1u);
-    if (l.line < (uint32_t)TOPL) return true;
+    if (l.line < (uint32_t)TOPL) { heap_hi = n0 + 1u; return true; }
     const uint32_t c = l.line >> LPC_SHIFT;
-    if (c < n_heap_chunks) return true;
+    if (c < n_heap_chunks) { heap_hi = n0 + 1u; return true; }
     if (c >= a->ht) return false;
     const uint32_t got = acquire_chunk();
     if (got == MAPAD_GPOOL_EMPTY) return false;
     table()[a->nt + c] = got;
     n_heap_chunks = c + 1;
+    heap_hi = n0 + 1u;
     return true;
   }
   MAPAD_DEV uint32_t min_cap() const { return a->max_nodes; }
@@ -305,6 +309,7 @@ struct GroupWorkspace {
     }
     n_node_chunks = 1;
     n_heap_chunks = 1;
+    heap_hi = 0;
   }
   struct Store {
     const GroupWorkspace* w;
@@ -842,6 +847,7 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
   Grp<G>::sync();
   ws.n_node_chunks = 1;
   ws.n_heap_chunks = 1;
+  ws.heap_hi = 0;
   ws.node0 = reinterpret_cast<typename GS::Node*>(a.pool.base + ((size_t)c_nodes << MAPAD_GCHUNK_SHIFT));
   ws.heap0 = reinterpret_cast<HeapEnt*>(a.pool.base + ((size_t)c_heap << MAPAD_GCHUNK_SHIFT));
   ws.top = smem_top;
