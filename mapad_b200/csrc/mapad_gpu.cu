@@ -230,6 +230,7 @@ struct mapad_gpu {
   PinBuf<char> h_text;
   PinBuf<Cursors> h_cur;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_wait = nullptr;  // blocking-sync event: a host thread waiting for a search launch (seconds to minutes) sleeps
   size_t ws_budget = 0;
 };
 
@@ -250,6 +251,14 @@ static int pick_device(int device, std::string& err) {
   return MAPAD_OK;
 }
 
+// Waits for the handle's stream without spinning: with one host thread per chunk in flight (and one process per GPU) the
+// default spin-wait of cudaStreamSynchronize would keep tens of host cores busy for the length of every search launch.
+static cudaError_t wait_stream(mapad_gpu* h) {
+  cudaError_t e = cudaEventRecord(h->ev_wait, h->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(h->ev_wait);
+}
+
 static int init_handle(mapad_gpu* h, int device) {
   h->device = device;
   CK(cudaSetDevice(device));
@@ -259,6 +268,7 @@ static int init_handle(mapad_gpu* h, int device) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
   for (auto& e : h->ev) CK(cudaEventCreate(&e));
+  CK(cudaEventCreateWithFlags(&h->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
   return MAPAD_OK;
 }
 
@@ -446,6 +456,7 @@ void mapad_gpu_destroy(mapad_gpu* h) {
   h->h_seq.release(); h->h_qual.release(); h->h_offsets.release(); h->h_seeds.release(); h->h_records.release();
   h->h_hits.release(); h->h_ops.release(); h->h_cigar.release(); h->h_text.release(); h->h_cur.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->ev_wait) cudaEventDestroy(h->ev_wait);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -503,26 +514,39 @@ static int upload_batch(mapad_gpu* h, const mapad_reads* in) {
 // ---- K2 driver: the group kernel (search_group.cuh) ---------------------------------------------
 // One launch maps every read of the batch; a read is only handed back (deferred) when the chunk pool runs dry, and
 // then re-run with fewer groups in flight, i.e. more pool per group.
-struct GroupShape { int g, topl; };
+#ifndef MAPAD_PREFETCH_WIDE_DEFAULT
+#define MAPAD_PREFETCH_WIDE_DEFAULT 0u
+#endif
+struct GroupShape { int g, topl, minb; };
 static GroupShape group_shape(bool wide) {  // tuning knobs, read per batch: MAPAD_GROUP = lanes per read, MAPAD_TOPL = heap lines in shared memory
   // defaults (profiles/r2_summary.md): small references (narrow layout, light reads) are issue-bound -> 4 lanes per read;
   // hg19-scale references (wide layout, reads of 1e5 - 1e7 frames) are bound by pool capacity and by the latency of
   // their heaviest reads -> one read per warp
-  GroupShape s{wide ? 32 : 4, 11};
+  GroupShape s{wide ? 32 : 4, 11, MAPAD_GROUP_MIN_BLOCKS};
   if (const char* e = getenv("MAPAD_GROUP")) s.g = atoi(e);
-  if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 32) s.g = wide ? 32 : 4;
-  s.topl = s.g == 1 ? 3 : (s.g == 32 ? 43 : 11);
-  if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43) s.topl = t; }
+  if (s.g != 1 && s.g != 4 && s.g != 8 && s.g != 16 && s.g != 32) s.g = wide ? 32 : 4;
+  s.topl = s.g == 1 ? 3 : (s.g >= 16 ? 43 : 11);
+  // one read per warp only: kernels compiled for 20 / 24 resident warps per SM (96 / 80 registers), MAPAD_GROUPS_PER_SM selects
+  if (const char* e = getenv("MAPAD_GROUPS_PER_SM")) { const int m = atoi(e); if (s.g == 32 && (m == 20 || m == 24)) s.minb = m; }
+  if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43 || t == 171) s.topl = t; }
+  if (s.topl == 171 && s.g != 32) s.topl = 43;  // 10.7 KiB of shared memory per read: only with one read per warp
   return s;
 }
 
-template <bool WIDE, int G, int TOPL>
+// Latency hiding for deep heaps (GroupLaunch::prefetch): bit 0 = next family lines of a trickle-down, bit 1 = occ blocks of
+// the popped frame.  MAPAD_TRICKLE_PREFETCH=<0..3> overrides the default (profiles/r2_summary.md).
+static uint32_t prefetch_mode(bool wide) {
+  if (const char* e = getenv("MAPAD_TRICKLE_PREFETCH")) return (uint32_t)atoi(e) & 3u;
+  return wide ? MAPAD_PREFETCH_WIDE_DEFAULT : 0u;
+}
+
+template <bool WIDE, int G, int TOPL, int MINB = MAPAD_GROUP_MIN_BLOCKS>
 static cudaError_t launch_group_kernel(const GroupLaunch<WIDE>& a, uint32_t n_groups, cudaStream_t stream) {
   constexpr int gpb = MAPAD_GROUP_BLOCK / G;
   const size_t smem = (size_t)gpb * TOPL * 64;
-  cudaError_t e = cudaFuncSetAttribute(k_search_group<WIDE, G, TOPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_search_group<WIDE, G, TOPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_search_group<WIDE, G, TOPL><<<n_groups / gpb, MAPAD_GROUP_BLOCK, smem, stream>>>(a);
+  k_search_group<WIDE, G, TOPL, MINB><<<n_groups / gpb, MAPAD_GROUP_BLOCK, smem, stream>>>(a);
   return cudaGetLastError();
 }
 template <bool WIDE>
@@ -531,7 +555,10 @@ static cudaError_t launch_group_dispatch(const GroupShape& sh, const GroupLaunch
   MAPAD_GROUP_CASE(1, 3); MAPAD_GROUP_CASE(1, 11);
   MAPAD_GROUP_CASE(4, 11);
   MAPAD_GROUP_CASE(8, 11); MAPAD_GROUP_CASE(8, 43);
-  MAPAD_GROUP_CASE(32, 43);
+  MAPAD_GROUP_CASE(16, 43);
+  if (sh.g == 32 && sh.topl == 43 && sh.minb == 20) return launch_group_kernel<WIDE, 32, 43, 20>(a, n_groups, stream);
+  if (sh.g == 32 && sh.topl == 43 && sh.minb == 24) return launch_group_kernel<WIDE, 32, 43, 24>(a, n_groups, stream);
+  MAPAD_GROUP_CASE(32, 43); MAPAD_GROUP_CASE(32, 171);
 #undef MAPAD_GROUP_CASE
   return launch_group_kernel<WIDE, 8, 11>(a, n_groups, stream);
 }
@@ -542,6 +569,7 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
   const uint64_t n = h->n_reads;
   GroupShape sh = group_shape(WIDE);
   if (sh.topl == 3 && sh.g != 1) sh.topl = 11;
+  if (sh.topl != 43) sh.minb = MAPAD_GROUP_MIN_BLOCKS;
   const uint32_t gpb = (uint32_t)(MAPAD_GROUP_BLOCK / sh.g);
   GroupLaunch<WIDE> a;
   a.ix = ix; a.P = P; a.rb = rb;
@@ -603,6 +631,7 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
     a.iter_budget = profile_iters;
     a.flags_or = attempt ? 2u : 0u;
     a.patient = serial ? 1u : 0u;
+    a.prefetch = prefetch_mode(WIDE);
     a.deferred_list = deferred;
     uint32_t n_def = 0;
     const uint32_t n_launches = serial ? n_work : 1u;
@@ -613,7 +642,7 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
       CK(launch_group_dispatch<WIDE>(sh, a, (uint32_t)(serial ? gpb : use), h->stream));
       ++launches;
       CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
+      CK(wait_stream(h));
       CK(cudaGetLastError());
       if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the search was cut short for profiling, no results"; return MAPAD_ELIMIT; }
       if (h->h_cur.p->overflow & MAPAD_POOL_TIMEOUT_FLAG) { h->err = "the device-wide chunk pool stayed empty for 20 s (workspace too small for the reads in flight)"; return MAPAD_ELIMIT; }
@@ -707,7 +736,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     }
     CK(cudaEventRecord(h->ev[4], h->stream));
     CK(cudaMemcpyAsync(h->h_cur.p, h->d_cur.p, sizeof(Cursors), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(wait_stream(h));
     CK(cudaGetLastError());
     trace("epilogue", n, 0, 0);
     const Cursors c = *h->h_cur.p;
@@ -742,7 +771,7 @@ static int run_batch(mapad_gpu* h, uint32_t flags, mapad_results* out) {
     out->text = h->h_text.p; out->n_text = c.text_cursor;
   }
   CK(cudaEventRecord(h->ev[5], h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(wait_stream(h));
   cudaEventElapsedTime(&out->ms_h2d, h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&out->ms_prologue, h->ev[1], h->ev[2]);
   cudaEventElapsedTime(&out->ms_search, h->ev[2], h->ev[3]);

@@ -199,6 +199,8 @@ struct GroupLaunch {
   uint32_t iter_budget;    // profiling aid: stop every group after this many expansions (0 = off)
   uint32_t flags_or;       // ORed into ReadMid::flags (bit 1: the read went through a retry launch)
   uint32_t patient;        // 1: never hand a read back, wait for the pool (last-resort launches)
+  uint32_t prefetch;       // latency hiding for deep heaps (bit 0: next family lines of a trickle-down, bit 1: the two
+                           // occ blocks of the popped frame while its heap is being repaired); see MAPAD_TRICKLE_PREFETCH
 };
 
 
@@ -423,10 +425,10 @@ MAPAD_DEV void extend_all_group(const DevIndex& ix, const BiIv& in, BiIv out[4],
 // Speculative prefetch of the heap lines the NEXT trickle-down step may need (it depends on which grandchild wins): with
 // at least four lanes per read, lane b asks for the family line of grandchild b while the current step is being decided,
 // so a descent through the pooled (HBM / L2) levels costs one memory latency per TWO steps.  Costs up to 4x the line
-// traffic of those levels and ~25 instructions per step; off by default, build with -DMAPAD_TRICKLE_PREFETCH=1 to compare.
-#ifndef MAPAD_TRICKLE_PREFETCH
-#define MAPAD_TRICKLE_PREFETCH 0  // measured (profiles/r2_summary.md): the kernel is issue-bound, the extra address arithmetic costs more than it hides
-#endif
+// traffic of those levels and ~25 instructions per step.  Run-time switch GroupLaunch::prefetch (host: MAPAD_TRICKLE_PREFETCH):
+// on small references the kernel is issue-bound and the extra address arithmetic costs more than it hides (-6 % on cfg3,
+// profiles/r2_summary.md); reads with heaps of 1e5 - 2e6 entries (hg19 scale) are bound by exactly these dependent
+// round trips.  Only descents of heaps that reach into pooled memory (n >= 8 * TOPL) prefetch at all.
 MAPAD_DEV void prefetch_line(const void* p) {
 #if defined(__CUDA_ARCH__)
   asm volatile("prefetch.L1 [%0];" ::"l"(p));
@@ -463,22 +465,40 @@ struct GroupSearch {
   MAPAD_DEV HeapEnt rd(uint32_t x1) const { const HLoc l = heap_loc(x1); return ws.line_ptr(l.line)[l.slot]; }
   MAPAD_DEV HeapEnt* ptr(uint32_t x1) const { const HLoc l = heap_loc(x1); return ws.line_ptr(l.line) + l.slot; }
 
+  // Requests the two occ blocks the expansion of node `nd` will read (extend_all_group: rows lower - 1 and lower + size - 1
+  // of the interval the extension starts from); even lanes ask for the first, odd lanes for the second.
+  MAPAD_DEV void prefetch_occ(const Node& nd, int L) const {
+    Frame f;
+    node_load(nd, 0u, f);
+    const bool forward = f.start <= L - f.start - f.len;
+    const uint64_t lower = forward ? f.iv.lower_rev : f.iv.lower;
+    const uint64_t r = (ws.gl & 1) ? lower + f.iv.size - 1u : (lower ? lower - 1u : 0u);
+    const DevIndex& ix = ws.a->ix;
+    prefetch_line(WIDE ? ix.occ() + (r >> 7) * 64 : ix.occ() + (r >> 6) * 32);
+  }
+
   // MinMaxHeap::trickle_down_max from 1-based position h (2 or 3: the top of the max levels) with `e` in the hole;
   // n = number of elements.  One family line per step.
-  MAPAD_DEV void trickle_max(uint32_t h, HeapEnt e, uint32_t n) {
+  // `occ_node` (optional): the node of the frame being popped; its two occ blocks are requested after the first round trip
+  // of the descent, so that their latency overlaps the remaining steps (the node was requested before the descent began).
+  MAPAD_DEV void trickle_max(uint32_t h, HeapEnt e, uint32_t n, const Node* occ_node, int L) {
     HeapEnt* hpos = ws.top + (h - 1u);
     uint32_t c_lo = 1u;  // C(level of h)
     bool synced = false;
+    const uint32_t pf = n >= 8u * (uint32_t)TOPL ? ws.a->prefetch : 0u;
+    bool occ_pending = (pf & 2u) != 0u && occ_node != nullptr;
     while (2u * h <= n) {
-      HeapEnt* ln = ws.line_ptr(h - c_lo);
+      const uint32_t line = h - c_lo;
+      HeapEnt* ln = ws.line_ptr(line);
       const HeapLine6 f = load_line6(ln);
-      if (MAPAD_TRICKLE_PREFETCH && G >= 4 && ws.gl < 4) {
+      if ((pf & 1u) && G >= 4 && ws.gl < 4) {
         const uint32_t g = 4u * h + (uint32_t)ws.gl;             // grandchild gl of h; its family line is needed if it has children
         const uint32_t gline = g - ((c_lo << 2) | 1u);
         if (2u * g <= n && gline >= (uint32_t)TOPL) prefetch_line(ws.line_ptr(gline));
       }
       Grp<G>::sync();  // every lane holds the line (and everything read before) — lane 0 may write now
       synced = true;
+      if (occ_pending && line >= (uint32_t)TOPL) { prefetch_occ(*occ_node, L); occ_pending = false; }
       int best = -1;
       float bk = e.score;
       if (4u * h + 3u <= n) {  // all six candidates exist (every step but the last one or two of a descent)
@@ -520,6 +540,7 @@ struct GroupSearch {
     HeapEnt c0 = ws.top[1], c1 = ws.top[2];
     uint32_t c_lo = 1u;  // C(level of the children of h)
     bool synced = false;
+    const uint32_t pf = n >= 8u * (uint32_t)TOPL ? ws.a->prefetch : 0u;
     while (2u * h <= n) {
       const uint32_t la = 2u * h - c_lo;
       HeapEnt* pa = ws.line_ptr(la);
@@ -530,7 +551,7 @@ struct GroupSearch {
       for (int c = 0; c < 6; ++c) { fa.x[c] = e; fb.x[c] = e; }
       if (4u * h <= n) fa = load_line6(pa);
       if (4u * h + 2u <= n) fb = load_line6(pb);
-      if (MAPAD_TRICKLE_PREFETCH && G >= 8 && ws.gl < 8) {
+      if ((pf & 1u) && G >= 8 && ws.gl < 8) {
         // the next step (at grandchild g) reads the family lines of 2g and 2g+1: eight candidates, one per lane
         const uint32_t g = 4u * h + ((uint32_t)ws.gl >> 1);
         const uint32_t gline = 2u * g - ((c_lo << 2) | 1u) + ((uint32_t)ws.gl & 1u);
@@ -711,7 +732,7 @@ struct GroupSearch {
     const uint32_t n1 = n - 1u;
     if (m <= n1) {
       const HeapEnt last = rd(n);
-      trickle_max(m, last, n1);
+      trickle_max(m, last, n1, &pn, job.L);
     }
     heap_n = n1;
     Frame sf;
@@ -942,8 +963,9 @@ MAPAD_DEV void group_search_lane(const GroupLaunch<WIDE>& a, uint32_t slot, int 
 #ifndef MAPAD_GROUP_MIN_BLOCKS
 #define MAPAD_GROUP_MIN_BLOCKS 16
 #endif
-template <bool WIDE, int G, int TOPL>
-__global__ void __launch_bounds__(MAPAD_GROUP_BLOCK, MAPAD_GROUP_MIN_BLOCKS) k_search_group(const __grid_constant__ GroupLaunch<WIDE> a) {
+// MINB = resident blocks (warps) per SM the register allocation is sized for: 16 -> up to 128 registers, 20 -> 96, 24 -> 80.
+template <bool WIDE, int G, int TOPL, int MINB = MAPAD_GROUP_MIN_BLOCKS>
+__global__ void __launch_bounds__(MAPAD_GROUP_BLOCK, MINB) k_search_group(const __grid_constant__ GroupLaunch<WIDE> a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t group_in_block = threadIdx.x / G;
   const uint32_t slot = blockIdx.x * (MAPAD_GROUP_BLOCK / G) + group_in_block;

@@ -194,6 +194,7 @@ int run_group(const DevIndex& ix, const BatchPrep& bp, const mapad_reads& in, co
   a.op_pool = op_pool.data(); a.op_cap = (uint32_t)op_pool.size();
   a.iter_budget = 0;
   a.flags_or = 0;
+  a.prefetch = 3u;  // the prefetch address arithmetic runs (and is bounds-checked by the sanitizer builds); the prefetch itself is a no-op here
   // the host's retry loop (mapad_gpu.cu::search_with_groups): reads handed back because the pool ran dry are re-run
   // with fewer groups in flight
   uint32_t total_deferred = 0;

@@ -161,8 +161,13 @@ def test_wide_layout_and_retry_launch(api):
     """64-bit block layout forced on a small index, and a chunk pool so small that it runs dry: reads are handed back
     and re-run with fewer groups in flight; results must not change.  Also every group size the library is built for."""
     out = _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1"})
-    for g in ("1", "4", "32"):
+    for g in ("1", "4", "16", "32"):
         _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_GROUP": g})
+    # latency-hiding variants of the one-read-per-warp kernel: heap-line + occ prefetch, 171 heap lines in shared memory,
+    # kernels compiled for 20 / 24 resident warps per SM
+    _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TRICKLE_PREFETCH": "3", "MAPAD_TOPL": "171"})
+    _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TRICKLE_PREFETCH": "3", "MAPAD_GROUPS_PER_SM": "24"})
+    _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TRICKLE_PREFETCH": "2", "MAPAD_GROUPS_PER_SM": "20"})
     # 16 groups own 32 of the 72 chunks (256 KiB each); the largest of these reads pops 3e5 frames, so the 40 pooled chunks
     # run dry while several groups grow at once (calibrated with the emulation: tests/test_group_kernel.py)
     out = _run_child(CHILD.replace("SPEC_EXTRA", "").replace("(30, 90)", "(50, 70)").replace("genome = random_genome(200000, seed=43)", "genome = random_genome(3000000, seed=43)"),
@@ -177,6 +182,11 @@ def test_search_limits_eviction(api):
     assert int(out.split("limit")[1].split()[0]) > 20, out
     out = _run_child(CHILD.replace("SPEC_EXTRA", "spec['limits'] = (300, 700); spec['abort'] = True"), {})
     assert int(out.split("limit")[1].split()[0]) > 20, out
+    # pop_min descents with the speculative line prefetch (heaps reaching below the shared-memory top)
+    out = _run_child(CHILD.replace("SPEC_EXTRA", "spec['limits'] = (300, 700)"), {"MAPAD_TRICKLE_PREFETCH": "3", "MAPAD_GROUP": "8"})
+    assert int(out.split("limit")[1].split()[0]) > 20, out
+    out = _run_child(CHILD.replace("SPEC_EXTRA", "spec['limits'] = (2000, 5000)"), {"MAPAD_TRICKLE_PREFETCH": "3", "MAPAD_FORCE_WIDE": "1"})
+    assert int(out.split("limit")[1].split()[0]) > 0, out
 
 
 def test_cfg3_size_index(api):

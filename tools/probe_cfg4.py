@@ -3,6 +3,7 @@
 (the bench's pipelining) and reports seconds, reads/s, frames/s, deferred reads.  Variants are NAME[:ENV=VALUE,...].
 Measurement tool — the numbers it prints are not bench values.
 Usage: python tools/probe_cfg4.py [K=8] [reads_per_chunk=25000] variant..."""
+import hashlib
 import json
 import os
 import sys
@@ -45,14 +46,19 @@ for v in variants:
     def work(i):
         res = mappers[i].map_raw(structs[i][0], 0)
         recs = abi._as_array(res.records, res.n_reads, abi.RECORD_DTYPE)
-        stats[i] = (int(recs["frames_popped"].astype(np.int64).sum()), int(((recs["flags"] & 2) != 0).sum()), time.time())
+        sig = hashlib.sha1()
+        for f in ("mapped", "tid", "pos", "strand", "mapq", "alignment_score", "nm", "x0", "x1", "best_lower", "best_size", "frames_popped"):
+            sig.update(np.ascontiguousarray(recs[f]).tobytes())
+        stats[i] = (int(recs["frames_popped"].astype(np.int64).sum()), int(((recs["flags"] & 2) != 0).sum()), time.time(), sig.hexdigest()[:12])
 
     t = time.time()
     th = [threading.Thread(target=work, args=(i,)) for i in range(K)]
     [x.start() for x in th]; [x.join() for x in th]
     dt = time.time() - t
     row = dict(variant=parts[0], env=env, seconds=round(dt, 2), reads_per_s=K * n_reads / dt, frames_per_s=sum(s[0] for s in stats.values()) / dt,
-               deferred=sum(s[1] for s in stats.values()), done_s=sorted(round(s[2] - t, 1) for s in stats.values()))
+               deferred=sum(s[1] for s in stats.values()), done_s=sorted(round(s[2] - t, 1) for s in stats.values()),
+               # records of every chunk hashed (best hit, position, MAPQ, scores, frame counts): must not change between variants
+               signature=hashlib.sha1("".join(stats[i][3] for i in range(K)).encode()).hexdigest()[:12])
     rows.append(row)
     print(json.dumps(row), flush=True)
     for m in mappers:
