@@ -446,7 +446,10 @@ def main():
         traffic, traffic_src = None, None
         try:  # DRAM bytes per popped frame of the search kernel from the committed `ncu` capture (profiles/)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-            traffic, traffic_src = tj["dram_bytes_per_frame"] * P / n_chunks_all, tj["source"]
+            per_frame = tj.get("by_workload", {}).get(args.workload)
+            if per_frame is not None:  # only a capture of THIS workload's index / heap regime is carried over
+                traffic = per_frame * P / n_chunks_all
+                traffic_src = tj.get("source_" + args.workload, tj["source"])
         except Exception:
             pass
         # the search launches of different chunks overlap on the device, so the dominant kernel's achieved rate is taken over

@@ -5,7 +5,8 @@
 
     python -m mapad_b200.cli index -g genome.fa [--seed 1234]      # writes genome.fa.{tbw,tle,toc,trt,tsa,tpi,tos}
 
-Flag names and defaults follow /root/reference/src/main.rs:96-300.  `map` loads the seven index files next to the
+Flag names, defaults and validators follow /root/reference/src/main.rs:30-303 (`-p` or `-c`/`-e`, probabilities checked
+to lie in [0, 1], `-v`, `--seed`; `--threads` / `--port` are accepted and unused).  `map` loads the seven index files next to the
 FASTA when they exist (as the reference does) and otherwise indexes the FASTA in memory.  Reads come from FASTQ,
 FASTQ.GZ or BAM (flags, auxiliary fields and the @PG/@RG/@CO header lines of a BAM input are carried over like in
 create_bam_header / create_bam_record).  Differences: CRAM is not read, and the per-read XD:f timing tag is not written.  Several chunks are kept in flight (--inflight) so that the
@@ -42,22 +43,44 @@ def read_fasta(path):
     return contigs
 
 
+def prob(raw):
+    """parse_validate_prob (src/main.rs:33-39): an f32 in [0, 1]."""
+    try:
+        v = float(raw)
+    except ValueError:
+        raise argparse.ArgumentTypeError("not a number: %r" % raw)
+    if not 0.0 <= v <= 1.0:
+        raise argparse.ArgumentTypeError("%r is not a probability (0 <= value <= 1)" % raw)
+    return v
+
+
 def build_parser():
     ap = argparse.ArgumentParser(prog="mapad_b200")
+    # global options of the reference (src/main.rs:63-98); --threads and --port have no meaning for the GPU path and are
+    # accepted so that existing command lines keep working
+    glob = argparse.ArgumentParser(add_help=False)
+    glob.add_argument("-v", action="count", default=0, help="Sets the level of verbosity")
+    glob.add_argument("--threads", type=int, default=1, help="accepted for compatibility (host threads only compress BAM blocks)")
+    glob.add_argument("--port", type=int, default=3130, help="accepted for compatibility (no TCP dispatcher: one box, --gpus N)")
+    glob.add_argument("--seed", type=int, default=1234, help="Seed for the random number generator")
     sub = ap.add_subparsers(dest="cmd", required=True)
-    m = sub.add_parser("map", help="Maps reads to a genome")
+    m = sub.add_parser("map", help="Maps reads to a genome", parents=[glob])
     m.add_argument("-r", "--reads", required=True)
     m.add_argument("-g", "--reference", required=True, help="FASTA file of the genome")
     m.add_argument("-o", "--output", required=True)
-    m.add_argument("-p", dest="poisson_prob", type=float, required=True)
-    m.add_argument("--library", choices=["single_stranded", "double_stranded"], required=True)
-    m.add_argument("-f", dest="five_prime_overhang", type=float, required=True)
-    m.add_argument("-t", dest="three_prime_overhang", type=float, default=None)
-    m.add_argument("-d", dest="ds_deamination_rate", type=float, required=True)
-    m.add_argument("-s", dest="ss_deamination_rate", type=float, required=True)
-    m.add_argument("-D", dest="divergence", type=float, default=0.02)
-    m.add_argument("-i", dest="indel_rate", type=float, required=True)
-    m.add_argument("-x", dest="gap_extension_penalty", type=float, default=1.0)
+    # -p (Discrete bound) and -c / -e (Continuous bound) exclude each other, one is required (src/main.rs:136-160, 456-476)
+    m.add_argument("-p", dest="poisson_prob", type=prob, default=None,
+                   help="Minimum probability of the number of mismatches under `-D` base error rate")
+    m.add_argument("-c", dest="as_cutoff", type=float, default=None, help="Per-base average alignment score cutoff (-c > AS / read_len^e ?)")
+    m.add_argument("-e", dest="as_cutoff_exponent", type=float, default=1.0, help="Exponent applied to the read length (ignored without -c)")
+    m.add_argument("-l", "--library", choices=["single_stranded", "double_stranded"], required=True)
+    m.add_argument("-f", dest="five_prime_overhang", type=prob, required=True)
+    m.add_argument("-t", dest="three_prime_overhang", type=prob, default=None)
+    m.add_argument("-d", dest="ds_deamination_rate", type=prob, required=True)
+    m.add_argument("-s", dest="ss_deamination_rate", type=prob, required=True)
+    m.add_argument("-D", dest="divergence", type=prob, default=0.02)
+    m.add_argument("-i", dest="indel_rate", type=prob, required=True)
+    m.add_argument("-x", dest="gap_extension_penalty", type=prob, default=1.0)
     m.add_argument("--batch_size", type=int, default=250000)
     m.add_argument("--ignore_base_quality", action="store_true")
     m.add_argument("--gap_dist_ends", type=int, default=5)
@@ -65,13 +88,11 @@ def build_parser():
     m.add_argument("--no_search_limit_recovery", action="store_true")
     m.add_argument("--force_overwrite", action="store_true")
     m.add_argument("-R", "--read_group", default=None, help="read group ID added to every record")
-    m.add_argument("--seed", type=int, default=1234)
     m.add_argument("--device", type=int, default=0, help="first CUDA device")
     m.add_argument("--gpus", type=int, default=1, help="shard every chunk of reads over this many GPUs of the box (devices --device ..)")
     m.add_argument("--inflight", type=int, default=8, help="chunks kept in flight per GPU")
-    ix = sub.add_parser("index", help="Indexes a genome file")
+    ix = sub.add_parser("index", help="Indexes a genome file", parents=[glob])
     ix.add_argument("-g", "--reference", required=True, help="FASTA file of the genome")
-    ix.add_argument("--seed", type=int, default=1234)
     ix.add_argument("--device", type=int, default=None, help="sort suffixes on this CUDA device (tie-free synthetic texts only; default: host SA-IS)")
     return ap
 
@@ -91,10 +112,17 @@ def run_index(a):
 def params_from_args(a):
     if a.library == "single_stranded" and a.three_prime_overhang is None:
         raise SystemExit("-t is required for --library single_stranded")
-    return api.params_from_cli(library=a.library, p=a.poisson_prob, f=a.five_prime_overhang, t=a.three_prime_overhang or 0.0,
-                               d=a.ds_deamination_rate, s=a.ss_deamination_rate, D=a.divergence, i=a.indel_rate,
-                               x=a.gap_extension_penalty, gap_dist_ends=a.gap_dist_ends, max_num_gaps_open=a.max_num_gaps_open,
-                               ignore_base_quality=a.ignore_base_quality, no_search_limit_recovery=a.no_search_limit_recovery)
+    if (a.poisson_prob is None) == (a.as_cutoff is None):
+        raise SystemExit("exactly one of -p (Poisson mismatch bound) and -c (alignment-score cutoff) is required")
+    P = api.params_from_cli(library=a.library, p=a.poisson_prob if a.poisson_prob is not None else 0.03, f=a.five_prime_overhang,
+                            t=a.three_prime_overhang or 0.0, d=a.ds_deamination_rate, s=a.ss_deamination_rate, D=a.divergence,
+                            i=a.indel_rate, x=a.gap_extension_penalty, gap_dist_ends=a.gap_dist_ends,
+                            max_num_gaps_open=a.max_num_gaps_open, ignore_base_quality=a.ignore_base_quality,
+                            no_search_limit_recovery=a.no_search_limit_recovery)
+    if a.as_cutoff is not None:  # Continuous::new(-c * -1.0, -e, representative mismatch penalty) (src/main.rs:463-475)
+        P.bound_kind = abi.BOUND_CONTINUOUS
+        P.cutoff, P.exponent = -float(a.as_cutoff), float(a.as_cutoff_exponent)
+    return P
 
 
 class _Shard:
@@ -213,7 +241,8 @@ def run_map(a, argv):
     if err is not None:
         print("mapad_b200: mapping failed: %s" % err, file=sys.stderr)
         return 1
-    print("mapped %d of %d reads (%d skipped on input)" % (state["mapped"], state["reads"], chunks.skipped), file=sys.stderr)
+    if a.v:
+        print("mapped %d of %d reads (%d skipped on input)" % (state["mapped"], state["reads"], chunks.skipped), file=sys.stderr)
     return 0
 
 

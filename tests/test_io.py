@@ -226,3 +226,29 @@ def test_bam_writer_threads_are_deterministic(tmp_path, monkeypatch):
     assert blobs[0] == blobs[1] and len(blobs[0]) > 100_000
     text, refs, recs = read_bam(str(tmp_path / "t5.bam"))
     assert len(recs) == 3 * len(seqs) and recs[-1]["name"] == "r%06d" % (len(seqs) - 1)
+
+
+def test_cli_flags_follow_reference():
+    """`mapad map` flag surface (src/main.rs:30-303): -p xor -c/-e, probability validators, -l, -v, global --seed/--threads."""
+    import pytest
+    from mapad_b200 import abi, cli
+    ap = cli.build_parser()
+    base = ["map", "-r", "r.fq", "-g", "g.fa", "-o", "o.bam", "-l", "single_stranded", "-f", "0.5", "-t", "0.5", "-d", "0.02", "-s", "1.0",
+            "-i", "0.001", "-x", "0.5"]
+    a = ap.parse_args(base + ["-p", "0.03", "-v", "-v", "--threads", "8", "--seed", "7"])
+    assert a.v == 2 and a.seed == 7 and a.library == "single_stranded"
+    P = cli.params_from_args(a)
+    assert P.bound_kind == abi.BOUND_DISCRETE and abs(P.poisson_threshold - 0.03) < 1e-7
+    a = ap.parse_args(base + ["-c", "0.8", "-e", "0.9"])
+    P = cli.params_from_args(a)
+    assert P.bound_kind == abi.BOUND_CONTINUOUS and abs(P.cutoff + 0.8) < 1e-6 and abs(P.exponent - 0.9) < 1e-6
+    with pytest.raises(SystemExit):   # neither -p nor -c
+        cli.params_from_args(ap.parse_args(base))
+    with pytest.raises(SystemExit):   # both
+        cli.params_from_args(ap.parse_args(base + ["-p", "0.03", "-c", "0.8"]))
+    with pytest.raises(SystemExit):   # not a probability
+        ap.parse_args(base + ["-p", "1.5"])
+    with pytest.raises(SystemExit):
+        ap.parse_args([x if x != "0.02" else "-0.1" for x in base] + ["-p", "0.03"])
+    ix = ap.parse_args(["index", "-g", "g.fa", "--seed", "5"])
+    assert ix.seed == 5

@@ -19,7 +19,7 @@ from mapad_b200 import api, workloads  # noqa: E402
 from helpers import product_params  # noqa: E402
 from ref_cases import cli_params  # noqa: E402
 
-cfg = workloads.CONFIGS["cfg3"]
+cfg = workloads.CONFIGS[os.environ.get("PROFILE_WORKLOAD", "cfg3")]  # cfg4: hg19 scale (index outside L2, deep heaps with enough MAPAD_PROFILE_ITERS)
 genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
 index = api.Index.build(workloads.split_contigs(genome, cfg["n_contigs"]), seed=1234, device=0)
 spec = dict(cli_params(cfg["library"]))
@@ -27,8 +27,10 @@ if os.environ.get("MAPAD_PROFILE_LIMITS"):  # e.g. "20000,100000": small STACK_L
     spec["limits"] = tuple(int(x) for x in os.environ["MAPAD_PROFILE_LIMITS"].split(","))
 mapper = api.Mapper(index, product_params(spec), device=0)
 len_range = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else cfg["len_range"]
-seq, qual, off = workloads.simulate_batch(genome, 250_000, len_range, seed=79, library=cfg["library"])
-R, keep = api.make_reads(seq, qual, off, np.arange(250_000, dtype=np.uint32))
+n_reads = int(os.environ.get("PROFILE_READS", "250000"))
+seq, qual, off = workloads.simulate_batch(genome, n_reads, len_range, seed=79, library=cfg["library"])
+del genome
+R, keep = api.make_reads(seq, qual, off, np.arange(n_reads, dtype=np.uint32))
 try:
     mapper.map_raw(R, 0)
     print("unexpected: the batch completed")
