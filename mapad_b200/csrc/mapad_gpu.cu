@@ -529,7 +529,12 @@ static GroupShape group_shape(bool wide) {  // tuning knobs, read per batch: MAP
   // one read per warp only: kernels compiled for 20 / 24 resident warps per SM (96 / 80 registers), MAPAD_GROUPS_PER_SM selects
   if (const char* e = getenv("MAPAD_GROUPS_PER_SM")) { const int m = atoi(e); if (s.g == 32 && (m == 20 || m == 24)) s.minb = m; }
   if (const char* e = getenv("MAPAD_TOPL")) { const int t = atoi(e); if (t == 3 || t == 11 || t == 43 || t == 171) s.topl = t; }
-  if (s.topl == 171 && s.g != 32) s.topl = 43;  // 10.7 KiB of shared memory per read: only with one read per warp
+  // instantiated combinations: G = 1: 3 | 11, G = 4: 11, G = 8: 11 | 43, G = 16: 43, G = 32: 11 | 43 | 171 (10.7 KiB per read)
+  if (s.g == 1 && s.topl > 11) s.topl = 11;
+  if (s.g == 4) s.topl = 11;
+  if (s.g == 8 && s.topl != 43) s.topl = 11;
+  if (s.g == 16) s.topl = 43;
+  if (s.g == 32 && s.topl == 3) s.topl = 11;
   return s;
 }
 
@@ -558,9 +563,9 @@ static cudaError_t launch_group_dispatch(const GroupShape& sh, const GroupLaunch
   MAPAD_GROUP_CASE(16, 43);
   if (sh.g == 32 && sh.topl == 43 && sh.minb == 20) return launch_group_kernel<WIDE, 32, 43, 20>(a, n_groups, stream);
   if (sh.g == 32 && sh.topl == 43 && sh.minb == 24) return launch_group_kernel<WIDE, 32, 43, 24>(a, n_groups, stream);
-  MAPAD_GROUP_CASE(32, 43); MAPAD_GROUP_CASE(32, 171);
+  MAPAD_GROUP_CASE(32, 11); MAPAD_GROUP_CASE(32, 43); MAPAD_GROUP_CASE(32, 171);
 #undef MAPAD_GROUP_CASE
-  return launch_group_kernel<WIDE, 8, 11>(a, n_groups, stream);
+  return cudaErrorInvalidConfiguration;  // group_shape() only produces the combinations above
 }
 
 template <bool WIDE>

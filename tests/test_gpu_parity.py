@@ -168,6 +168,7 @@ def test_wide_layout_and_retry_launch(api):
     _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TRICKLE_PREFETCH": "3", "MAPAD_TOPL": "171"})
     _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TRICKLE_PREFETCH": "3", "MAPAD_GROUPS_PER_SM": "24"})
     _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TRICKLE_PREFETCH": "2", "MAPAD_GROUPS_PER_SM": "20"})
+    _run_child(CHILD.replace("SPEC_EXTRA", ""), {"MAPAD_FORCE_WIDE": "1", "MAPAD_TOPL": "11"})
     # 16 groups own 32 of the 72 chunks (256 KiB each); the largest of these reads pops 3e5 frames, so the 40 pooled chunks
     # run dry while several groups grow at once (calibrated with the emulation: tests/test_group_kernel.py)
     out = _run_child(CHILD.replace("SPEC_EXTRA", "").replace("(30, 90)", "(50, 70)").replace("genome = random_genome(200000, seed=43)", "genome = random_genome(3000000, seed=43)"),

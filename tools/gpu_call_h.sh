@@ -23,6 +23,7 @@ M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__inst_e
 T=$(left 480); [ $T -gt 0 ] && ( time PROFILE_WORKLOAD=cfg4 PROFILE_READS=25000 MAPAD_PROFILE_ITERS=40000 MAPAD_WS_BYTES=$((40<<30)) timeout $T ncu --metrics $M --clock-control none \
     -k regex:k_search_group -c 1 --csv --log-file gpurun_out/h_cfg4_saturated_metrics.csv python tools/profile_saturated.py 86 100 ) > gpurun_out/h_ncu_cfg4.log 2>&1
 tail -3 gpurun_out/h_ncu_cfg4.log | cut -c1-400
-# same-box A/B: 16 vs 24 resident warps per SM on 12 chunks of 25 000 reads
-T=$(left 560); [ $T -gt 0 ] && ( time timeout $T python tools/probe_cfg4.py 12 25000 w16 w24:MAPAD_GROUPS_PER_SM=24 ) > gpurun_out/h_probe.log 2> gpurun_out/h_probe.err
+# same-box tuning probe, 16 chunks of 25 000 reads as in calls F0 / G (base there: 184 s): 24 resident warps per SM; 11 heap
+# lines in shared memory (more L1 for the pooled heap lines)
+T=$(left 600); [ $T -gt 0 ] && ( time timeout $T python tools/probe_cfg4.py 16 25000 w24:MAPAD_GROUPS_PER_SM=24 t11:MAPAD_TOPL=11 ) > gpurun_out/h_probe.log 2> gpurun_out/h_probe.err
 tail -3 gpurun_out/h_probe.log | cut -c1-700
