@@ -54,3 +54,36 @@ def test_no_device_no_compute():
     with pytest.raises(api.MapadError) as e:
         api.Mapper(index, api.params_from_cli())
     assert e.value.code == -2  # MAPAD_ENODEV: no CPU fallback
+
+
+def _c_struct_fields(header, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        # "float a, b, c" / "const uint8_t* seq" / "uint64_t less[8]" / "mapad_alt alts[2]"
+        first, *rest = [x.strip() for x in decl.split(",")]
+        fields.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[\d+\])?$", first)[0])
+        fields += [re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[\d+\])?$", r)[0] for r in rest]
+    return fields
+
+
+def test_rust_binding_covers_header():
+    """bindings/rust/mapad-gpu-sys (the thin FFI crate of the north star; not compilable here: no Rust toolchain) declares
+    every function of include/mapad_gpu.h and mirrors every POD field for field, in order."""
+    header = open(os.path.join(ROOT, "include", "mapad_gpu.h")).read()
+    rust = open(os.path.join(ROOT, "bindings", "rust", "mapad-gpu-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\b(mapad_[a-z0-9_]+)\s*\(", header)) - {"mapad_sdm_get_fn", "mapad_sdm_start_fn"}
+    bound = set(re.findall(r"pub fn (mapad_[a-z0-9_]+)\s*\(", rust))
+    assert declared == bound, declared ^ bound
+    for name in ("mapad_params", "mapad_index_view", "mapad_reads", "mapad_edit_op", "mapad_hit", "mapad_alt", "mapad_record", "mapad_results"):
+        want = _c_struct_fields(header, name)
+        body = re.search(r"pub struct %s \{(.*?)\n\}" % name, rust, re.S).group(1)
+        got = re.findall(r"pub ([a-z0-9_]+):", body)
+        assert want == got, (name, want, got)
+    for const, value in re.findall(r"(MAPAD_[A-Z0-9_]+) = (-?\d+)u?", header):
+        m = re.search(r"pub const %s: \w+ = (-?\d+);" % const, rust)
+        assert m and int(m.group(1)) == int(value), const
