@@ -175,7 +175,7 @@ MAPAD_DEV float d_get(const float* dcomp, int L, int split, int backward_index, 
 // ---------------------------------------------------------------------------------------------
 // Search state containers
 // ---------------------------------------------------------------------------------------------
-struct HeapEnt { float score; uint32_t node; };
+struct alignas(8) HeapEnt { float score; uint32_t node; };  // 8-byte aligned: one 64-bit load / store per entry
 
 enum { GAP_INS = 0, GAP_DEL = 1, GAP_CLOSED = 2 };
 
@@ -272,6 +272,40 @@ MAPAD_DEV void node_store(NodeW32& dst, const Frame& f, uint32_t parent, uint32_
   n.ngaps = (uint8_t)f.ngaps; n.pad0 = 0; n.pad1 = 0;
   dst = n;
 }
+// The 32 bytes of a node as they lie in memory (little endian), assembled in registers: building a node struct field by field
+// made the compiler keep it in local memory (byte stores, 30 local stores and 266 L2 write sectors per popped frame in the
+// ncu capture profiles/r2_g32_wide_50Mbp_raw.csv); a node is written with two 16-byte stores instead.
+struct NodeWords { uint32_t w0, w1, w2, w3, w4, w5, w6, w7; };
+MAPAD_DEV NodeWords node_words(const NodeT<false>*, const Frame& f, uint32_t parent, uint32_t op) {
+  NodeWords v;
+  v.w0 = parent; v.w1 = op;
+  v.w2 = (uint32_t)f.iv.lower; v.w3 = (uint32_t)f.iv.lower_rev; v.w4 = (uint32_t)f.iv.size;
+  v.w5 = ((uint32_t)f.start & 0xffffu) | ((uint32_t)f.len << 16);
+  v.w6 = ((uint32_t)f.gap_f & 0xffu) | (((uint32_t)f.gap_b & 0xffu) << 8) | (((uint32_t)f.ngaps & 0xffu) << 16);
+  v.w7 = 0u;
+  return v;
+}
+MAPAD_DEV NodeWords node_words(const NodeW32*, const Frame& f, uint32_t parent, uint32_t op) {
+  NodeWords v;
+  v.w0 = parent; v.w1 = op;
+  v.w2 = (uint32_t)f.iv.lower; v.w3 = (uint32_t)f.iv.lower_rev; v.w4 = (uint32_t)f.iv.size;
+  v.w5 = ((uint32_t)(f.iv.lower >> 32) & 0xffu) | (((uint32_t)(f.iv.lower_rev >> 32) & 0xffu) << 8) |
+         (((uint32_t)(f.iv.size >> 32) & 0xffu) << 16) | (((uint32_t)(f.gap_f | (f.gap_b << 2)) & 0xffu) << 24);
+  v.w6 = ((uint32_t)f.start & 0xffffu) | ((uint32_t)f.len << 16);
+  v.w7 = (uint32_t)f.ngaps & 0xffu;
+  return v;
+}
+MAPAD_DEV void node_put(void* dst, const NodeWords& v) {  // dst is 16-byte aligned (nodes are alignas(16), 32 B)
+#if defined(__CUDA_ARCH__)
+  uint4* q = reinterpret_cast<uint4*>(dst);
+  q[0] = make_uint4(v.w0, v.w1, v.w2, v.w3);
+  q[1] = make_uint4(v.w4, v.w5, v.w6, v.w7);
+#else
+  uint32_t* q = reinterpret_cast<uint32_t*>(dst);
+  q[0] = v.w0; q[1] = v.w1; q[2] = v.w2; q[3] = v.w3; q[4] = v.w4; q[5] = v.w5; q[6] = v.w6; q[7] = v.w7;
+#endif
+}
+
 template <class N>
 MAPAD_DEV void node_load(const N& src, uint32_t id, Frame& f) {
   N n = src;

@@ -140,15 +140,18 @@ MAPAD_DEV int ffs32(uint32_t x) {  // 1-based index of the lowest set bit, 0 if 
   return __builtin_ffs((int)x);
 #endif
 }
+// Straight-line code on purpose: the lanes of a group call this with different positions (the ancestor chain of a push), and a
+// branch per special case made them diverge (heap_loc + line_ptr: 24 % of all warp instructions at 13 of 32 active threads,
+// profiles/r2_g32_wide_50Mbp_hotspots.txt).
 MAPAD_HD HLoc heap_loc(uint32_t x) {
-  if (x < 4u) return HLoc{0u, x - 1u};
+  const bool small = x < 4u;
   const int lvl = 31 - clz32(x);
   const uint32_t odd = (uint32_t)lvl & 1u;
   const uint32_t owner = x >> (1u + odd);
   const uint32_t slot = odd ? 2u + (x & 3u) : (x & 1u);
-  const int lo = lvl - 1 - (int)odd;
-  const uint32_t c = 0x55555555u & ((2u << lo) - 1u);
-  return HLoc{owner - c, slot};
+  const int lo = lvl - 1 - (int)odd;                              // < 0 only for x < 4
+  const uint32_t c = 0x55555555u & ((2u << (lo < 0 ? 0 : lo)) - 1u);
+  return HLoc{small ? 0u : owner - c, small ? x - 1u : slot};
 }
 // number of lines that positions 1..n occupy
 MAPAD_HD uint32_t heap_lines_for(uint32_t n) {
@@ -244,12 +247,25 @@ struct GroupWorkspace {
     const uint32_t c = table()[id >> NPC_SHIFT];
     return reinterpret_cast<Node*>(a->pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT))[id & ((1u << NPC_SHIFT) - 1u)];
   }
+  // The pooled storage is addressed by the plain line number (lines < TOPL are unused there).  Selects instead of branches
+  // (see heap_loc); only the chunk-table lookup of lines beyond chunk 0 is conditional.
   MAPAD_DEV HeapEnt* line_ptr(uint32_t line) const {
-    if (line < (uint32_t)TOPL) return top + (line << 3);
-    const uint32_t g = line;  // the pooled storage is addressed by the plain line number (lines < TOPL unused there)
-    if (g < (1u << LPC_SHIFT)) return heap0 + ((size_t)g << 3);
-    const uint32_t c = table()[a->nt + (g >> LPC_SHIFT)];
-    return reinterpret_cast<HeapEnt*>(a->pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT)) + ((size_t)(g & ((1u << LPC_SHIFT) - 1u)) << 3);
+    static_assert((uint32_t)TOPL <= (1u << LPC_SHIFT), "the shared-memory lines are a prefix of chunk 0's line numbers");
+    const bool in_top = line < (uint32_t)TOPL;
+    const bool in0 = line < (1u << LPC_SHIFT);
+    uint32_t c = 0u;
+    if (!in0) c = table()[a->nt + (line >> LPC_SHIFT)];
+    uint8_t* chunk = in0 ? reinterpret_cast<uint8_t*>(heap0) : a->pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT);
+    uint8_t* base = in_top ? reinterpret_cast<uint8_t*>(top) : chunk;
+    const uint32_t idx = in0 ? line : (line & ((1u << LPC_SHIFT) - 1u));
+    return reinterpret_cast<HeapEnt*>(base + ((size_t)idx << 6));
+  }
+  MAPAD_DEV Node* node_ptr(uint32_t id) const {
+    const bool in0 = id < (1u << NPC_SHIFT);
+    uint32_t c = 0u;
+    if (!in0) c = table()[id >> NPC_SHIFT];
+    uint8_t* chunk = in0 ? reinterpret_cast<uint8_t*>(node0) : a->pool.base + ((size_t)c << MAPAD_GCHUNK_SHIFT);
+    return reinterpret_cast<Node*>(chunk) + (in0 ? id : (id & ((1u << NPC_SHIFT) - 1u)));
   }
   MAPAD_DEV HeapEnt* slot_ptr(uint32_t i0) const {  // 0-based logical index
     const HLoc l = heap_loc(i0 + 1u);
@@ -513,12 +529,16 @@ struct GroupSearch {
         }
       }
       if (best < 0) break;
-      const HeapEnt be = f.x[best];
+      // select chains instead of f.x[best]: a dynamically indexed register array goes through local memory (6 local stores
+      // + 2 local loads per step = 245 L1 / 266 L2 write sectors per popped frame in profiles/r2_g32_wide_50Mbp_raw.csv)
+      HeapEnt be = f.x[0];
+#pragma unroll
+      for (int c = 1; c < 6; ++c) if (best == c) be = f.x[c];
       wr(hpos, be);
       hpos = ln + best;
       if (best < 2) break;  // moved to a child: done
       const int pc = (best - 2) >> 1;  // the grandchild's parent is one of the two children in the same line
-      const HeapEnt pe = f.x[pc];
+      const HeapEnt pe = pc ? f.x[1] : f.x[0];
       if (pe.score > e.score) { wr(ln + pc, e); e = pe; }
       h = 4u * h + (uint32_t)(best - 2);
       c_lo = (c_lo << 2) | 1u;
@@ -603,12 +623,12 @@ struct GroupSearch {
   // the parent, lanes [0, G/2) fetch the chain of x and lanes [G/2, G) the chain of p in the same round trip, a vote finds
   // where the climb stops, and the lanes whose ancestors move one chain level down write them in parallel.  Deeper chains
   // (more than G/2 levels) continue with all G lanes on the chosen chain.
-  MAPAD_DEV void push(HeapEnt e, const Node& nd) {
+  MAPAD_DEV void push(HeapEnt e, const NodeWords& nd) {
     const uint32_t x = heap_n + 1u;
     heap_n = x;
     Grp<G>::sync();  // writes of the previous phase are visible
     if (x == 1u) {
-      if (ws.gl == 0) { ws.node(e.node) = nd; ws.top[0] = e; }
+      if (ws.gl == 0) { node_put(ws.node_ptr(e.node), nd); ws.top[0] = e; }
       return;
     }
     const uint32_t p = x >> 1;
@@ -622,7 +642,7 @@ struct GroupSearch {
         const HeapEnt ae = rd(c >> 2);
         if (climb_max ? (e.score > ae.score) : (e.score < ae.score)) { t += 1; c >>= 2; } else break;
       }
-      ws.node(e.node) = nd;
+      node_put(ws.node_ptr(e.node), nd);
       uint32_t cur = x;
       if (moved) { *ptr(x) = pe; cur = p; }
       for (uint32_t k = 0; k < t; ++k) { *ptr(cur) = *ptr(cur >> 2); cur >>= 2; }
@@ -659,7 +679,7 @@ struct GroupSearch {
       base += (uint32_t)G;
     }
     if (gl == 0) {
-      ws.node(e.node) = nd;
+      node_put(ws.node_ptr(e.node), nd);
       if (moved) *ptr(x) = pe;
       *ptr(cur0 >> (2u * total)) = e;
     }
@@ -672,9 +692,8 @@ struct GroupSearch {
     root.iv = BiIv{0, 0, ix.m.n};
     root.start = start_pos; root.len = 0; root.gap_f = GAP_CLOSED; root.gap_b = GAP_CLOSED; root.ngaps = 0;
     root.score = 0.0f; root.node = 0;
-    Node nd;
-    node_store(nd, root, 0, pack_op(0, MAPAD_ED_MATCH, 0));  // tree.clear(): root = NodeId(0)
-    push(HeapEnt{0.0f, 0}, nd);
+    // tree.clear(): root = NodeId(0)
+    push(HeapEnt{0.0f, 0}, node_words(static_cast<const Node*>(nullptr), root, 0, pack_op(0, MAPAD_ED_MATCH, 0)));
     Grp<G>::sync();  // the root is visible to every lane before the first step reads it
   }
 
@@ -692,12 +711,11 @@ struct GroupSearch {
       node_hi += 1;
     }
     tree_len += 1;
-    Node nd;
-    node_store(nd, f, parent_node, op);
+    const NodeWords nd = node_words(static_cast<const Node*>(nullptr), f, parent_node, op);
     if (f.len == L) {  // a hit: std BinaryHeap::push
       Grp<G>::sync();
       if (ws.gl == 0) {
-        ws.node(id) = nd;
+        node_put(ws.node_ptr(id), nd);
         if (n_hits < MAPAD_MAX_HITS) {
           HitTmp h;
           h.score = f.score; h.node = id; h.lower = f.iv.lower; h.lower_rev = f.iv.lower_rev; h.size = f.iv.size;
