@@ -53,8 +53,8 @@ CPU_LABEL = "C++ restatement of mapAD 0.45.0 (reference binary not buildable her
 
 
 def cli_spec(library):
-    from ref_cases import cli_params
-    return cli_params(library)
+    from mapad_b200 import specs
+    return specs.cli_spec(library)
 
 
 class ClockSampler:
@@ -230,9 +230,9 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from compare import mismatching_reads
-    from helpers import product_params
+    from compare import mismatching_reads  # pure numpy record comparison (tests/compare.py)
     from mapad_b200 import api
+    from mapad_b200.specs import product_params  # oracle-free: the oracle is only loaded by the CPU legs below (run_cpu)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")

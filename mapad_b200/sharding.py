@@ -38,7 +38,6 @@ def broadcast_index_blob(dist, meta_bytes, blob_tensor, src=0):
 
 def _rebase(res, hit_base, op_base, cig_base, text_base):
     rec = res.records.copy()
-    mapped = rec["mapped"] != 0
     rec["cigar_off"] += np.uint32(cig_base)
     rec["md_off"] += np.uint32(text_base)
     rec["hit_off"] += np.uint32(hit_base)
@@ -48,7 +47,6 @@ def _rebase(res, hit_base, op_base, cig_base, text_base):
     hits = res.hits.copy()
     if len(hits):
         hits["edit_off"] += np.uint32(op_base)
-    del mapped
     return rec, hits
 
 

@@ -14,24 +14,7 @@ from oracle import oracle as ora  # noqa: E402  (test infrastructure)
 f32 = np.float32
 
 
-def _model_div(model):
-    """`0.02 / 3.0` in the reference is an f32 division."""
-    if model[0] == "simple":
-        m = list(model)
-        if isinstance(m[6], float) and abs(m[6] - 0.02 / 3.0) < 1e-12:
-            m[6] = float(f32(0.02) / f32(3.0))
-        return tuple(m)
-    return model
-
-
-def resolve_gap(v, repr_mm):
-    if isinstance(v, tuple):
-        if v[0] == "repr":
-            return float(f32(v[1]) * f32(repr_mm)) if v[1] != 1.0 else float(f32(repr_mm))
-        if v[0] == "log2":
-            return float(ora.lib().ora_log2f(f32(v[1])))
-        raise ValueError(v)
-    return float(v)
+from mapad_b200.specs import model_div as _model_div, product_params, resolve_gap  # noqa: E402,F401  (oracle-free, shared with bench / tools)
 
 
 def oracle_params(spec):
@@ -58,46 +41,6 @@ def oracle_params(spec):
         p.limits(*spec["limits"])
     p.repr_mm = repr_mm
     return p
-
-
-def product_params(spec):
-    """Same spec -> mapad_b200.abi.Params (the C-ABI POD)."""
-    from mapad_b200 import abi, api
-
-    model = _model_div(spec["model"])
-    P = abi.Params()
-    if model[0] == "test":
-        P.model_kind = abi.MODEL_TEST
-        P.test_deam_score, P.test_mm_score, P.test_match_score = model[1], model[2], model[3]
-    elif model[0] == "vindija":
-        P.model_kind = abi.MODEL_VINDIJA_PWM
-    else:
-        P.model_kind = abi.MODEL_SIMPLE_ADNA
-        P.library = abi.LIB_SINGLE_STRANDED if model[1] == "single_stranded" else abi.LIB_DOUBLE_STRANDED
-        P.five_prime_overhang, P.three_prime_overhang = model[2], model[3]
-        P.ds_deamination_rate, P.ss_deamination_rate, P.divergence = model[4], model[5], model[6]
-        P.ignore_base_quality = int(model[7])
-    repr_mm = api.representative_mismatch_penalty(P)
-    P.representative_mismatch_penalty = repr_mm
-    b = spec["bound"]
-    if b[0] == "test":
-        P.bound_kind = abi.BOUND_TEST
-        P.test_threshold = b[1]
-        P.test_representative_mm = repr_mm if b[2] is None else b[2]
-    elif b[0] == "discrete":
-        P.bound_kind = abi.BOUND_DISCRETE
-        P.poisson_threshold, P.base_error_rate = b[1], b[2]
-    else:
-        P.bound_kind = abi.BOUND_CONTINUOUS
-        P.cutoff, P.exponent = b[1], b[2]
-    g = spec["gaps"]
-    P.penalty_gap_open = resolve_gap(g[0], repr_mm)
-    P.penalty_gap_extend = resolve_gap(g[1], repr_mm)
-    P.gap_dist_ends, P.max_num_gaps_open = g[2], g[3]
-    P.stack_limit_abort = int(spec.get("abort", False))
-    if "limits" in spec:
-        P.stack_limit, P.edit_tree_limit = spec["limits"]
-    return P
 
 
 def revcomp(s):

@@ -87,3 +87,28 @@ def test_rust_binding_covers_header():
     for const, value in re.findall(r"(MAPAD_[A-Z0-9_]+) = (-?\d+)u?", header):
         m = re.search(r"pub const %s: \w+ = (-?\d+);" % const, rust)
         assert m and int(m.group(1)) == int(value), const
+
+
+def test_cli_spec_equals_params_from_cli():
+    """specs.product_params(specs.cli_spec(lib)) — what bench.py and the GPU tests use — is byte for byte what the C-ABI's own
+    mapad_params_from_cli derives from the same flags (src/main.rs:418-499)."""
+    from mapad_b200 import specs
+    for lib in ("single_stranded", "double_stranded"):
+        a = specs.product_params(specs.cli_spec(lib))
+        b = api.params_from_cli(library=lib, p=0.03, f=0.5, t=0.5, d=0.02, s=1.0, D=0.02, i=0.001, x=0.5)
+        assert bytes(a) == bytes(b), lib
+
+
+def test_product_modules_do_not_load_the_oracle():
+    """The oracle is test infrastructure: importing the product package, its spec helpers, the measurement tools' imports and
+    bench.py itself must not load it (bench.py only does inside its CPU legs)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests'); sys.argv = ['bench.py']\n"
+            "import mapad_b200.api, mapad_b200.specs, mapad_b200.cli, mapad_b200.sharding, mapad_b200.workloads, compare\n"
+            "import importlib.util as u; s = u.spec_from_file_location('bench_mod', %r + '/bench.py'); m = u.module_from_spec(s); s.loader.exec_module(m)\n"
+            "mapad_b200.specs.product_params(mapad_b200.specs.cli_spec('single_stranded'))\n"
+            "bad = [k for k in sys.modules if k == 'oracle' or k.startswith('oracle.') or k == 'helpers']\n"
+            "assert not bad, bad\n" % (ROOT, ROOT, ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

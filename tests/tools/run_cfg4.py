@@ -3,7 +3,7 @@
 against the oracle on a sample of reads (positions beyond 2^32, wide 64 B occ blocks, HBM-resident index), then maps one
 chunk per search-kernel variant and records reads/s, frames/s and the per-read frame counts (gpurun_out/cfg4_frames.npz).
 Measurement tool — the numbers it prints are not bench values.
-Usage: python tools/run_cfg4.py [genome_bp] [n_reads] [n_parity] [variants, e.g. 8,32,1]"""
+Usage: python tests/tools/run_cfg4.py [genome_bp] [n_reads] [n_parity] [variants, e.g. 8,32,1]"""
 import json
 import os
 import sys
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

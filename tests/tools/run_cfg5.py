@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
-"""BASELINE cfg5: backtracking stress sweep on the hg19-scale index — `-p` x read length, reporting reads/s, search-frame
+"""(Test infrastructure: uses the CPU oracle as the checker / CPU column, hence under tests/.)
+BASELINE cfg5: backtracking stress sweep on the hg19-scale index — `-p` x read length, reporting reads/s, search-frame
 counts and the achieved fraction of the memory roofline per cell, with the CPU restatement beside it on a small sample.
 Cells are time-boxed (chunks of reads are mapped until the cell's budget is used or its read target is reached), because
 the work per read spans five orders of magnitude over the grid.  Measurement tool — writes gpurun_out/cfg5_sweep.json and a
 markdown table; the numbers are not bench values.
-Usage: python tools/run_cfg5.py [genome_bp=3.1e9] [seconds_per_cell=15] [max_reads_per_cell=100000] [cpu_reads=200]"""
+Usage: python tests/tools/run_cfg5.py [genome_bp=3.1e9] [seconds_per_cell=15] [max_reads_per_cell=100000] [cpu_reads=200]"""
 import json
 import os
 import sys
@@ -13,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

@@ -17,8 +17,7 @@ os.environ.setdefault("MAPAD_GROUP", "32")
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30000
 genome_bp = int(float(sys.argv[2])) if len(sys.argv) > 2 else 20_000_000
 from mapad_b200 import api, workloads  # noqa: E402
-from helpers import product_params  # noqa: E402
-from ref_cases import cli_params  # noqa: E402
+from mapad_b200.specs import cli_spec as cli_params, product_params  # noqa: E402  (oracle-free)
 
 genome = workloads.random_genome_array(genome_bp, seed=42)
 index = api.Index.build(workloads.split_contigs(genome, 4), seed=1234, device=0)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 ( time timeout 1500 python -X faulthandler -m pytest tests -m gpu -q ) > gpurun_out/b_pytest.log 2>&1
 tail -6 gpurun_out/b_pytest.log
-( time MAPAD_TRACE=1 timeout 1000 python -X faulthandler tools/run_cfg4.py 3.1e9 20000 300 8,32 ) > gpurun_out/b_cfg4.log 2>&1
+( time MAPAD_TRACE=1 timeout 1000 python -X faulthandler tests/tools/run_cfg4.py 3.1e9 20000 300 8,32 ) > gpurun_out/b_cfg4.log 2>&1
 grep -v "mapad trace" gpurun_out/b_cfg4.log | tail -5
 NCU="ncu --set full --clock-control none --import-source on -k regex:k_search_group -c 1"
 MAPAD_GROUP=1 timeout 600 $NCU -f -o gpurun_out/r2_g1_cfg3 python tools/profile_saturated.py > gpurun_out/b_ncu_g1.log 2>&1

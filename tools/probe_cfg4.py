@@ -17,8 +17,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from mapad_b200 import abi, api, workloads  # noqa: E402
-from helpers import product_params  # noqa: E402
-from ref_cases import cli_params  # noqa: E402
+from mapad_b200.specs import cli_spec as cli_params, product_params  # noqa: E402  (oracle-free)
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 25_000

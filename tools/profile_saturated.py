@@ -16,8 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ.setdefault("MAPAD_WS_BYTES", str(60 << 30))
 os.environ.setdefault("MAPAD_PROFILE_ITERS", "3000")
 from mapad_b200 import api, workloads  # noqa: E402
-from helpers import product_params  # noqa: E402
-from ref_cases import cli_params  # noqa: E402
+from mapad_b200.specs import cli_spec as cli_params, product_params  # noqa: E402  (oracle-free)
 
 cfg = workloads.CONFIGS[os.environ.get("PROFILE_WORKLOAD", "cfg3")]  # cfg4: hg19 scale (index outside L2, deep heaps with enough MAPAD_PROFILE_ITERS)
 genome = workloads.random_genome_array(cfg["genome_bp"], seed=42)
