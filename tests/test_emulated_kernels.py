@@ -60,6 +60,30 @@ def test_index_cross_check():
             assert emu.sa_get(index, row, layout) == oix.sa_get(row), (layout, row)
 
 
+def test_index_cross_check_5mbp():
+    """The two independent indexers (product: SA-IS; oracle: its own suffix sorter) on a 5 Mbp text with 1 kbp tandem repeats,
+    a palindromic stretch and N runs on both sides of the 20 bp threshold — a size and a repeat structure at which different
+    suffix-sorting strategies would diverge if either were wrong."""
+    g = random_genome(5_000_000, seed=21)
+    unit = g[1000:2000]
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    pal = g[7000:7400]
+    pal = pal + "".join(comp[c] for c in reversed(pal))
+    g = g[:300_000] + unit * 6 + g[300_000:1_200_000] + "N" * 37 + g[1_200_000:2_500_000] + pal + g[2_500_000:4_000_000] + "N" * 7 + unit * 3 + g[4_000_000:]
+    contigs = [("c1", g[:2_000_000]), ("c2", g[2_000_000:])]
+    draws = "ACGTTGCA"
+    index = api.Index.build(contigs, draws=draws)
+    oix = ora.OracleIndex.build(contigs, draws=draws)
+    a = index.arrays()
+    assert a["n"] == oix.n == 2 * len(g) + 2
+    assert np.array_equal(a["bwt"], oix.bwt())
+    assert a["less"][: len(oix.less())] == oix.less()
+    assert a["sentinel_rows"] == oix.sentinel_rows()
+    assert np.array_equal(a["sa_sample"], oix.sa_samples())
+    assert [tuple(x) for x in a["extra_rows"].tolist()] == oix.extra_rows()
+    assert dict(zip(a["orig_pos"].tolist(), a["orig_sym"].tolist())) == oix.original_symbols()
+
+
 def test_bench_reads_and_integration():
     data = json.load(open(os.path.join(GOLDEN, "ref_test_bench.json")))
     index = api.Index.build([("ref", data["ref_seq"])])
