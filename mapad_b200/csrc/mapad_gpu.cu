@@ -650,7 +650,7 @@ static int search_with_groups(mapad_gpu* h, const DevIndex& ix, const DevParams&
       CK(wait_stream(h));
       CK(cudaGetLastError());
       if (profile_iters) { h->err = "MAPAD_PROFILE_ITERS is set: the search was cut short for profiling, no results"; return MAPAD_ELIMIT; }
-      if (h->h_cur.p->overflow & MAPAD_POOL_TIMEOUT_FLAG) { h->err = "the device-wide chunk pool stayed empty for minutes while a group waited for its base chunks (workspace too small for the reads in flight)"; return MAPAD_ELIMIT; }
+      if (h->h_cur.p->overflow & MAPAD_POOL_TIMEOUT_FLAG) { h->err = "the device-wide chunk pool stayed empty for 20 s (workspace too small for the reads in flight)"; return MAPAD_ELIMIT; }
       n_def = h->h_cur.p->n_deferred;
       if (serial && n_def) { h->err = "a read exceeded the search workspace even with the whole pool to itself"; return MAPAD_ELIMIT; }
     }

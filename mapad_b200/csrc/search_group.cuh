@@ -175,12 +175,7 @@ template <bool WIDE> struct GNodeOf { using type = NodeT<false>; };
 template <> struct GNodeOf<true> { using type = NodeW32; };
 
 #define MAPAD_POOL_TIMEOUT_FLAG 4u   // Cursors::overflow bit: a group found no base chunks within the start-up patience
-#define MAPAD_PATIENCE_MAX 10000000u // frames from which a read waits "for good" (a read at EDIT_TREE_LIMIT pops 1e7 frames)
-// Bound of a wait "for good" (base chunks of a starting group, reads beyond MAPAD_PATIENCE_MAX frames, last-resort launches), in
-// back-off rounds of >= 2 us: >= 5 minutes.  At hg19 scale the reads in limit recovery of 20 chunks in flight can hold the whole
-// pool for longer than a minute (each owns 336 MB for >= 93 s); a group that starts in that phase holds nothing and must wait,
-// not fail the batch (the bound was 20 s until the end of round 2).
-#define MAPAD_WAIT_FOR_GOOD 150000000u
+#define MAPAD_PATIENCE_MAX 10000000u // back-off rounds of 2 us: 20 s
 // Everything one launch needs (passed by value as the kernel parameter).
 template <bool WIDE>
 struct GroupLaunch {
@@ -238,7 +233,7 @@ struct GroupWorkspace {
   // popped, at least 0.4 ms — young reads step aside first.  (Ten rounds per frame were measured: reads then sleep on their
   // memory for seconds and the GPU idles.)
   MAPAD_DEV uint32_t patience() const {
-    if (a->patient || frames >= MAPAD_PATIENCE_MAX) return MAPAD_WAIT_FOR_GOOD;
+    if (a->patient || frames >= MAPAD_PATIENCE_MAX) return MAPAD_PATIENCE_MAX;
     uint32_t p = frames < 200u ? 200u : frames;
 #if !defined(__CUDA_ARCH__)
     if (G == 1) p = 0;               // the emulation runs per-thread groups one after the other: nobody to wait for
